@@ -1,0 +1,214 @@
+/* pose_refine_b200.h -- C ABI of libpose_refine_b200.so (sm_100a).
+ *
+ * This is the drop-in boundary for pose_refine's data-parallel hot path: the batched depth
+ * rasteriser (cuda_renderer) and the point-to-plane ICP inner loop (cuda_icp).  The reference
+ * has no FFI layer -- its boundary is the C++ header API of two static libraries
+ * (cuda_renderer/renderer.h, cuda_icp/icp.h, cuda_icp/scene/...).  Each entry point below names
+ * the reference interface (file:line under the reference tree) it replaces; the C++ headers in
+ * include/pose_refine/ re-create the reference's own names on top of these calls.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `*_dev` pointers are device memory on the current device,
+ *     `*_host` pointers are host memory; pr_stream_t is a cudaStream_t (0 = default stream).
+ *   - every call returns 0 (PR_OK), a negative PR_ERR_* code, or a positive cudaError_t value.
+ *     Nothing exits the process (the reference's gpuErrchk does, renderer.cu:4-12).
+ *   - calls are asynchronous on `stream` unless their comment says they synchronise.
+ *   - no hidden allocation: scratch memory is caller-provided (`*_workspace_bytes` tells how much),
+ *     except for the pr_refiner_* convenience object, which owns its buffers.
+ *   - units follow the reference: meshes and rendered depth in millimetres, clouds in metres.
+ */
+#ifndef POSE_REFINE_B200_H
+#define POSE_REFINE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PR_OK 0
+#define PR_ERR_INVALID_ARGUMENT (-1)
+#define PR_ERR_UNSUPPORTED (-2)
+#define PR_ERR_WORKSPACE_TOO_SMALL (-3)
+#define PR_ERR_CAPACITY (-4)
+#define PR_ERR_IO (-5)
+#define PR_ERR_NO_DEVICE (-6)
+
+typedef struct CUstream_st* pr_stream_t;
+
+/* Model::ROI, cuda_renderer/renderer.h:43-48.  width<=0 or height<=0 means "no ROI". */
+typedef struct pr_roi { int x, y, width, height; } pr_roi;
+
+/* ICPConvergenceCriteria, cuda_icp/icp.h:38-50 (defaults 1e-5, 1e-5, 30). */
+typedef struct pr_icp_criteria {
+    float relative_fitness;
+    float relative_rmse;
+    int max_iteration;
+} pr_icp_criteria;
+
+/* RegistrationResult, cuda_icp/icp.h:26-36: row-major 4x4, inlier_rmse_, fitness_ (72 bytes). */
+typedef struct pr_registration_result {
+    float transformation[16];
+    float inlier_rmse;
+    float fitness;
+} pr_registration_result;
+
+/* Scene_projective, cuda_icp/scene/depth_scene/depth_scene.h:7-15.  pcd/normal: width*height
+ * Vec3f (3 packed floats) each, organised row-major, in DEVICE memory owned by the caller. */
+typedef struct pr_scene_projective {
+    uint64_t width, height;
+    float max_dist_diff;
+    float K[9];
+    const float* pcd_dev;
+    const float* normal_dev;
+} pr_scene_projective;
+
+/* Node_kdtree, cuda_icp/scene/pcd_scene/pcd_scene.h:5-25 (52 bytes, same field order). */
+typedef struct pr_node_kdtree {
+    int parent, child1, child2;
+    float split_v;
+    float bbox[6];
+    int split_dim;
+    int left, right;
+} pr_node_kdtree;
+
+/* Scene_nn, cuda_icp/scene/pcd_scene/pcd_scene.h:47-58: leaf-ordered points + normals + nodes in
+ * DEVICE memory owned by the caller (KDTree_cuda, pcd_scene.h:37-43). */
+typedef struct pr_scene_nn {
+    float max_dist_diff;
+    const float* pcd_dev;
+    const float* normal_dev;
+    const pr_node_kdtree* nodes_dev;
+    uint64_t n_points, n_nodes;
+} pr_scene_nn;
+
+/* ---------------------------------------------------------------------------------------- */
+/* library                                                                                    */
+int pr_version(void);
+const char* pr_error_string(int status);
+/* PR_OK iff the current CUDA device can run this library (compute capability 10.x). */
+int pr_device_check(void);
+
+/* ---------------------------------------------------------------------------------------- */
+/* mesh ingestion: replaces cuda_renderer::Model::LoadModel (renderer.cpp:16-58, assimp).       */
+/* Reads an ASCII or binary_little_endian PLY; writes triangles in face order as 9 floats each  */
+/* (Model::Triangle, renderer.h:60-70).  Call with tris_host == NULL to get the count.          */
+int pr_load_ply(const char* path, float* tris_host, size_t capacity_tris, size_t* n_tris);
+
+/* compute_proj, cuda_renderer/renderer.cpp:161-185 (host, pure arithmetic). */
+int pr_compute_proj(const float K[9], int width, int height, float near_plane, float far_plane, float proj[16]);
+
+/* ---------------------------------------------------------------------------------------- */
+/* rasteriser: replaces render_cuda_keep_in_gpu / render_cuda (renderer.cu:189-336) and the     */
+/* render_triangle kernel (renderer.cu:83-187).                                                 */
+/*   tris_dev   n_tris * 9 floats;  poses: n_poses row-major 4x4 (Model::mat4x4), host or device */
+/*   out_depth_dev  n_poses * W' * H' int32 (W',H' = ROI size when a ROI is given), 0 = empty    */
+/* Output equals render_cpu (renderer.cpp:259-298) bit for bit.                                 */
+size_t pr_render_workspace_bytes(size_t n_poses, size_t n_tris, size_t width, size_t height);
+int pr_render_batch(const float* tris_dev, size_t n_tris, const float* poses, int poses_on_device, size_t n_poses,
+                    size_t width, size_t height, const float proj[16], pr_roi roi, int32_t* out_depth_dev,
+                    void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
+
+/* raw2depth_uint16_cuda / raw2mask_uint8_cuda / raw2depth_mask_cuda (renderer.cu:338-439):      */
+/* depth = uint16_t(raw), mask = raw > 0 ? 255 : 0.  Either output may be NULL.                  */
+int pr_raw2depth_mask(const int32_t* raw_dev, size_t n, uint16_t* depth_dev, uint8_t* mask_dev, pr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------- */
+/* depth2cloud: replaces depth2cloud_cuda<T> (icp.cu:228-291) for a batch of n_images images.    */
+/* Cloud i is out_pts_dev[3*offsets[i] .. 3*(offsets[i]+counts[i])), row-major valid-pixel order. */
+/* Offsets are rounded up to a multiple of `align_points` (use 4 for 16-byte aligned clouds).    */
+/* stride must be 1 (stride > 1 indexes out of bounds upstream, icp.cpp:77-82).                  */
+/*   step 1 (count):  counts_dev[n_images], offsets_dev[n_images + 1] (last = total, padded).    */
+/*                    capacity_points (0 = unlimited): a cloud that would end beyond it is        */
+/*                    emptied (counts[i] = 0) and *overflow_dev (nullable) is set to 1, so the    */
+/*                    fill step and ICP stay in bounds without a host round trip.                 */
+/*   step 2 (fill):   writes the points of every cloud that fits.                                 */
+size_t pr_depth2cloud_workspace_bytes(size_t n_images, uint32_t width, uint32_t height);
+int pr_depth2cloud_count(const void* depth_dev, int depth_is_int32, size_t n_images, uint32_t width, uint32_t height,
+                         uint32_t stride, uint32_t align_points, size_t capacity_points, uint32_t* counts_dev,
+                         uint32_t* offsets_dev, uint32_t* overflow_dev,
+                         void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
+int pr_depth2cloud_fill(const void* depth_dev, int depth_is_int32, size_t n_images, uint32_t width, uint32_t height,
+                        const float K[9], uint32_t stride, uint32_t tl_x, uint32_t tl_y,
+                        const uint32_t* offsets_dev, float* out_pts_dev, size_t capacity_points,
+                        const void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------- */
+/* scene preparation (one-time per scene)                                                      */
+/* Scene_projective::init_Scene_projective_cuda (depth_scene.cu:3-20 -> depth_scene.cpp:3-35):   */
+/* organised cloud (dep2pcd, common.h:47-61) + LINEMOD-style normals (get_normal,               */
+/* common.cpp:17-107), computed on the device from a DEVICE depth image (uint16 or int32, mm).  */
+int pr_scene_projective_init(const void* depth_dev, int depth_is_int32, uint32_t width, uint32_t height,
+                             const float K[9], float* pcd_dev, float* normal_dev, pr_stream_t stream);
+
+/* Scene_nn::init_Scene_nn_cuda (pcd_scene.cu:3-20 -> pcd_scene.cpp:4-184): compacts the valid    */
+/* pixels, builds the kd-tree on the HOST with the reference's level-by-level algorithm          */
+/* (leaf <= max_leaf points) and returns host arrays the caller uploads.  Synchronous.           */
+/*   depth_host: uint16 or int32; pcd/normal_host: capacity_points*3 floats; nodes_host:          */
+/*   capacity_nodes nodes (2*n_points+1 always suffices).                                        */
+int pr_scene_nn_build_host(const void* depth_host, int depth_is_int32, uint32_t width, uint32_t height,
+                           const float K[9], int max_leaf, float* pcd_host, float* normal_host, size_t capacity_points,
+                           pr_node_kdtree* nodes_host, size_t capacity_nodes, size_t* n_points, size_t* n_nodes);
+
+/* ---------------------------------------------------------------------------------------- */
+/* ICP: replaces ICP_Point2Plane_cuda<Scene> (icp.cu:156-223), thrust__pcd2Ab (icp.h:128-209),   */
+/* Scene_*::query (depth_scene.h:30-48, pcd_scene.h:61-136), transform_pcd_cuda (icp.cu:142-153) */
+/* and eigen_slover_666 (icp.cpp:29-45) for a ragged batch of hypotheses, entirely on device.    */
+/*   pts_dev     packed Vec3f points; hypothesis h owns [offsets[h], offsets[h]+counts[h])        */
+/*   results_dev n_hyp records; flags: PR_ICP_UPDATE_POINTS writes the refined points back        */
+/*               (the reference mutates the model cloud in place, icp.cu:209).                    */
+#define PR_ICP_UPDATE_POINTS 1
+size_t pr_icp_workspace_bytes(size_t n_hyp, size_t capacity_points);
+int pr_icp_projective_batch(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_dev, size_t n_hyp,
+                            size_t capacity_points, const pr_scene_projective* scene, pr_icp_criteria criteria,
+                            pr_registration_result* results_dev, int flags,
+                            void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
+int pr_icp_nn_batch(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_dev, size_t n_hyp,
+                    size_t capacity_points, const pr_scene_nn* scene, pr_icp_criteria criteria,
+                    pr_registration_result* results_dev, int flags,
+                    void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
+
+/* eigen_slover_666 (icp.cpp:29-45) on the host: A 6x6 symmetric (36 floats), b 6 -> row-major 4x4. */
+int pr_solve_666(const float A[36], const float b[6], float T[16]);
+
+/* one reduction pass of thrust__pcd2Ab over one cloud (icp.cu:170-172): out29_dev[29].  Debug /   */
+/* parity entry point; synchronous-free.                                                         */
+int pr_pcd2ab_projective(const float* pts_dev, size_t n, const pr_scene_projective* scene, float* out29_dev,
+                         pr_stream_t stream);
+int pr_pcd2ab_nn(const float* pts_dev, size_t n, const pr_scene_nn* scene, float* out29_dev, pr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------- */
+/* pr_refiner: the whole path for one mesh + one scene behind a single call with HOST buffers -- */
+/* what PoseRenderer (pose_renderer.h:9-32) plus the test.cpp:143-172 sequence do upstream:       */
+/* render(poses) -> depth2cloud -> ICP_Point2Plane, for a batch of pose hypotheses.               */
+typedef struct pr_refiner pr_refiner;
+
+/* Uploads the mesh once (tris_host: n_tris*9 floats, mm). max_hyp bounds the batch size;          */
+/* capacity_points bounds the total number of model points of a batch (0 = max_hyp * W*H/4).      */
+/* A run whose clouds do not fit returns PR_ERR_CAPACITY (host variant) after emptying the clouds  */
+/* that spilled.                                                                                 */
+int pr_refiner_create(pr_refiner** out, const float* tris_host, size_t n_tris, uint32_t width, uint32_t height,
+                      const float K[9], size_t max_hyp, size_t capacity_points);
+void pr_refiner_destroy(pr_refiner* r);
+/* Scene from a HOST depth image (uint16 or int32, mm), prepared on the device.                  */
+int pr_refiner_set_scene_projective(pr_refiner* r, const void* depth_host, int depth_is_int32, float max_dist_diff);
+int pr_refiner_set_scene_nn(pr_refiner* r, const void* depth_host, int depth_is_int32);
+/* poses_host: n_hyp row-major 4x4 (model -> camera, mm).  results_host: n_hyp records.           */
+/* Copies poses H2D, runs render -> cloud -> ICP on `stream`, copies results D2H, synchronises.    */
+int pr_refiner_run(pr_refiner* r, const float* poses_host, size_t n_hyp, pr_icp_criteria criteria,
+                   pr_registration_result* results_host, pr_stream_t stream);
+/* Same with everything resident: poses_dev / results_dev on the device, no copies, no sync.     */
+int pr_refiner_run_device(pr_refiner* r, const float* poses_dev, size_t n_hyp, pr_icp_criteria criteria,
+                          pr_registration_result* results_dev, pr_stream_t stream);
+/* Introspection for tests and bench: device pointers into the refiner's own buffers, valid until */
+/* the next run: depth (n_hyp*W*H int32), points, offsets (n_hyp+1), counts (n_hyp).              */
+int pr_refiner_buffers(pr_refiner* r, const int32_t** depth_dev, const float** pts_dev,
+                       const uint32_t** offsets_dev, const uint32_t** counts_dev);
+/* kernel launches issued by this library since load (all entry points), for bench accounting.    */
+uint64_t pr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSE_REFINE_B200_H */

@@ -1,0 +1,87 @@
+"""ctypes binding of libpose_refine_b200.so -- one prototype per symbol of include/pose_refine_b200.h."""
+import ctypes as C
+import os
+
+from .build import LIB
+
+
+class Criteria(C.Structure):  # pr_icp_criteria
+    _fields_ = [("relative_fitness", C.c_float), ("relative_rmse", C.c_float), ("max_iteration", C.c_int)]
+
+
+class Roi(C.Structure):  # pr_roi
+    _fields_ = [("x", C.c_int), ("y", C.c_int), ("width", C.c_int), ("height", C.c_int)]
+
+
+class SceneProjective(C.Structure):  # pr_scene_projective
+    _fields_ = [("width", C.c_uint64), ("height", C.c_uint64), ("max_dist_diff", C.c_float), ("K", C.c_float * 9),
+                ("pcd_dev", C.c_void_p), ("normal_dev", C.c_void_p)]
+
+
+class SceneNN(C.Structure):  # pr_scene_nn
+    _fields_ = [("max_dist_diff", C.c_float), ("pcd_dev", C.c_void_p), ("normal_dev", C.c_void_p),
+                ("nodes_dev", C.c_void_p), ("n_points", C.c_uint64), ("n_nodes", C.c_uint64)]
+
+
+_vp, _sz, _i, _u32, _f = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_float
+_fp = C.POINTER(C.c_float)
+
+# every exported symbol of include/pose_refine_b200.h: name -> (restype, argtypes)
+PROTOTYPES = {
+    "pr_version": (_i, []),
+    "pr_error_string": (C.c_char_p, [_i]),
+    "pr_device_check": (_i, []),
+    "pr_load_ply": (_i, [C.c_char_p, _vp, _sz, C.POINTER(_sz)]),
+    "pr_compute_proj": (_i, [_vp, _i, _i, _f, _f, _vp]),
+    "pr_render_workspace_bytes": (_sz, [_sz, _sz, _sz, _sz]),
+    "pr_render_batch": (_i, [_vp, _sz, _vp, _i, _sz, _sz, _sz, _vp, Roi, _vp, _vp, _sz, _vp]),
+    "pr_raw2depth_mask": (_i, [_vp, _sz, _vp, _vp, _vp]),
+    "pr_depth2cloud_workspace_bytes": (_sz, [_sz, _u32, _u32]),
+    "pr_depth2cloud_count": (_i, [_vp, _i, _sz, _u32, _u32, _u32, _u32, _sz, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pr_depth2cloud_fill": (_i, [_vp, _i, _sz, _u32, _u32, _vp, _u32, _u32, _u32, _vp, _vp, _sz, _vp, _sz, _vp]),
+    "pr_scene_projective_init": (_i, [_vp, _i, _u32, _u32, _vp, _vp, _vp, _vp]),
+    "pr_scene_nn_build_host": (_i, [_vp, _i, _u32, _u32, _vp, _i, _vp, _vp, _sz, _vp, _sz, C.POINTER(_sz), C.POINTER(_sz)]),
+    "pr_icp_workspace_bytes": (_sz, [_sz, _sz]),
+    "pr_icp_projective_batch": (_i, [_vp, _vp, _vp, _sz, _sz, C.POINTER(SceneProjective), Criteria, _vp, _i, _vp, _sz, _vp]),
+    "pr_icp_nn_batch": (_i, [_vp, _vp, _vp, _sz, _sz, C.POINTER(SceneNN), Criteria, _vp, _i, _vp, _sz, _vp]),
+    "pr_solve_666": (_i, [_vp, _vp, _vp]),
+    "pr_pcd2ab_projective": (_i, [_vp, _sz, C.POINTER(SceneProjective), _vp, _vp]),
+    "pr_pcd2ab_nn": (_i, [_vp, _sz, C.POINTER(SceneNN), _vp, _vp]),
+    "pr_refiner_create": (_i, [C.POINTER(_vp), _vp, _sz, _u32, _u32, _vp, _sz, _sz]),
+    "pr_refiner_destroy": (None, [_vp]),
+    "pr_refiner_set_scene_projective": (_i, [_vp, _vp, _i, _f]),
+    "pr_refiner_set_scene_nn": (_i, [_vp, _vp, _i]),
+    "pr_refiner_run": (_i, [_vp, _vp, _sz, Criteria, _vp, _vp]),
+    "pr_refiner_run_device": (_i, [_vp, _vp, _sz, Criteria, _vp, _vp]),
+    "pr_refiner_buffers": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "pr_launch_count": (C.c_uint64, []),
+}
+
+_dll = None
+
+
+def lib():
+    """The loaded library; raises (never falls back) when it has not been built."""
+    global _dll
+    if _dll is None:
+        if not os.path.exists(LIB):
+            raise ImportError(
+                f"{LIB} is missing: build it with `python -m pose_refine_b200.build` "
+                "(nvcc, sm_100a). pose_refine_b200 has no CPU fallback.")
+        dll = C.CDLL(LIB)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(dll, name)  # AttributeError if the header and the library disagree
+            fn.restype, fn.argtypes = res, args
+        _dll = dll
+    return _dll
+
+
+class PoseRefineError(RuntimeError):
+    def __init__(self, status, where):
+        self.status = status
+        super().__init__(f"{where}: {lib().pr_error_string(status).decode()} (status {status})")
+
+
+def check(status, where):
+    if status != 0:
+        raise PoseRefineError(status, where)

@@ -1,0 +1,50 @@
+// common.cuh -- shared helpers for the sm_100a kernels of libpose_refine_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <atomic>
+
+#include "../../include/pose_refine_b200.h"
+
+namespace prb {
+
+// every kernel launch of the library goes through this counter (pr_launch_count)
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define PR_CUDA_TRY(expr)                                  \
+    do {                                                   \
+        cudaError_t pr_e_ = (expr);                        \
+        if (pr_e_ != cudaSuccess) return (int)pr_e_;       \
+    } while (0)
+
+#define PR_LAUNCH_CHECK()                                  \
+    do {                                                   \
+        cudaError_t pr_e_ = cudaPeekAtLastError();         \
+        if (pr_e_ != cudaSuccess) return (int)pr_e_;       \
+    } while (0)
+
+inline cudaStream_t as_stream(pr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kNumSMs = 148;  // B200
+
+// IEEE single ops that the compiler may never contract into FMA: the rasteriser and the cloud /
+// scene-preparation kernels use them so their results equal the reference's x86 CPU build
+// (no FMA there: -O3 without -march) bit for bit.
+__device__ __forceinline__ float mulf(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float addf(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float subf(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float divf(float a, float b) { return __fdiv_rn(a, b); }
+
+// x86 cvttss2si semantics for float -> int32 (what the reference's CPU build gets where C++
+// leaves the conversion undefined): NaN / out of range -> INT_MIN.
+__device__ __forceinline__ int f2i_x86(float v) {
+    return (v > -2147483904.0f && v < 2147483648.0f) ? __float2int_rz(v) : INT_MIN;
+}
+
+struct alignas(16) Mat34 {  // rows 0..2 of a row-major 4x4 rigid transform
+    float m[12];
+};
+
+}  // namespace prb

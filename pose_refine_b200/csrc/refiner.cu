@@ -1,0 +1,218 @@
+// refiner.cu -- the whole hot path behind one call: render -> depth2cloud -> ICP.
+//
+// pr_refiner is the batch counterpart of what the reference wires by hand in test.cpp:143-172
+// (render_cuda_keep_in_gpu -> depth2cloud_cuda -> init_Scene_*_cuda -> ICP_Point2Plane_cuda) and
+// of PoseRenderer (pose_renderer.h:9-32), which uploads the mesh once and renders batches of poses.
+// It owns every device buffer it needs (allocated once at create / set_scene), so a run is a fixed
+// sequence of launches on one stream with no allocation and no host round trip; the host variant
+// adds the pose upload (H2D) and the result download (D2H) and synchronises once at the end.
+//
+// Also here: library-level entry points (version, error strings, device check).
+#include "common.cuh"
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <new>
+
+struct pr_refiner {
+    uint32_t W = 0, H = 0;
+    float K[9];
+    float proj[16];
+    size_t n_tris = 0, max_hyp = 0, capacity_points = 0;
+    float* d_tris = nullptr;
+    float* d_poses = nullptr;
+    int32_t* d_depth = nullptr;
+    float* d_pts = nullptr;
+    uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_overflow = nullptr;
+    pr_registration_result* d_results = nullptr;
+    void *ws_render = nullptr, *ws_cloud = nullptr, *ws_icp = nullptr;
+    size_t ws_render_bytes = 0, ws_cloud_bytes = 0, ws_icp_bytes = 0;
+    // scene
+    int scene_kind = -1;   // 0 projective, 1 nn
+    float* d_scene_pcd = nullptr;
+    float* d_scene_nrm = nullptr;
+    pr_node_kdtree* d_nodes = nullptr;
+    pr_scene_projective sp;
+    pr_scene_nn sn;
+    uint32_t* h_overflow = nullptr;   // pinned
+};
+
+namespace {
+
+void free_scene(pr_refiner* r) {
+    cudaFree(r->d_scene_pcd); cudaFree(r->d_scene_nrm); cudaFree(r->d_nodes);
+    r->d_scene_pcd = nullptr; r->d_scene_nrm = nullptr; r->d_nodes = nullptr;
+    r->scene_kind = -1;
+}
+
+int run_device(pr_refiner* r, const float* poses_dev, size_t n_hyp, pr_icp_criteria crit,
+               pr_registration_result* results_dev, cudaStream_t stream) {
+    pr_stream_t s = reinterpret_cast<pr_stream_t>(stream);
+    pr_roi none = {0, 0, 0, 0};
+    int rc = pr_render_batch(r->d_tris, r->n_tris, poses_dev, 1, n_hyp, r->W, r->H, r->proj, none, r->d_depth,
+                             r->ws_render, r->ws_render_bytes, s);
+    if (rc != PR_OK) return rc;
+    rc = pr_depth2cloud_count(r->d_depth, 1, n_hyp, r->W, r->H, 1, 4, r->capacity_points, r->d_counts, r->d_offsets,
+                              r->d_overflow, r->ws_cloud, r->ws_cloud_bytes, s);
+    if (rc != PR_OK) return rc;
+    rc = pr_depth2cloud_fill(r->d_depth, 1, n_hyp, r->W, r->H, r->K, 1, 0, 0, r->d_offsets, r->d_pts, r->capacity_points,
+                             r->ws_cloud, r->ws_cloud_bytes, s);
+    if (rc != PR_OK) return rc;
+    if (r->scene_kind == 0)
+        return pr_icp_projective_batch(r->d_pts, r->d_offsets, r->d_counts, n_hyp, r->capacity_points, &r->sp, crit, results_dev, 0,
+                                       r->ws_icp, r->ws_icp_bytes, s);
+    return pr_icp_nn_batch(r->d_pts, r->d_offsets, r->d_counts, n_hyp, r->capacity_points, &r->sn, crit, results_dev, 0,
+                           r->ws_icp, r->ws_icp_bytes, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pr_version(void) { return 100; }   // 0.1.0
+
+const char* pr_error_string(int status) {
+    switch (status) {
+    case PR_OK: return "ok";
+    case PR_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case PR_ERR_UNSUPPORTED: return "unsupported (e.g. depth2cloud stride != 1)";
+    case PR_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
+    case PR_ERR_CAPACITY: return "output capacity exceeded";
+    case PR_ERR_IO: return "i/o error";
+    case PR_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+    }
+    if (status > 0) return cudaGetErrorString((cudaError_t)status);
+    return "unknown error";
+}
+
+int pr_device_check(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return PR_ERR_NO_DEVICE; }
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { cudaGetLastError(); return PR_ERR_NO_DEVICE; }
+    return (p.major == 10) ? PR_OK : PR_ERR_NO_DEVICE;
+}
+
+int pr_refiner_create(pr_refiner** out, const float* tris_host, size_t n_tris, uint32_t width, uint32_t height,
+                      const float K[9], size_t max_hyp, size_t capacity_points) {
+    if (!out || !tris_host || !K || n_tris == 0 || width == 0 || height == 0 || max_hyp == 0) return PR_ERR_INVALID_ARGUMENT;
+    int rc = pr_device_check();
+    if (rc != PR_OK) return rc;
+    pr_refiner* r = new (std::nothrow) pr_refiner();
+    if (!r) return PR_ERR_INVALID_ARGUMENT;
+    r->W = width; r->H = height; r->n_tris = n_tris; r->max_hyp = max_hyp;
+    memcpy(r->K, K, 36);
+    pr_compute_proj(K, (int)width, (int)height, 10.f, 10000.f, r->proj);
+    const size_t n_px = (size_t)width * height;
+    // default: room for every hypothesis covering a quarter of the image
+    r->capacity_points = capacity_points ? capacity_points : (max_hyp * (n_px / 4 + 4));
+    r->ws_render_bytes = pr_render_workspace_bytes(max_hyp, n_tris, width, height);
+    r->ws_cloud_bytes = pr_depth2cloud_workspace_bytes(max_hyp, width, height);
+    r->ws_icp_bytes = pr_icp_workspace_bytes(max_hyp, r->capacity_points);
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 256); };
+    alloc((void**)&r->d_tris, n_tris * 36);
+    alloc((void**)&r->d_poses, max_hyp * 64);
+    alloc((void**)&r->d_depth, max_hyp * n_px * 4);
+    alloc((void**)&r->d_pts, r->capacity_points * 12 + 64);
+    alloc((void**)&r->d_counts, max_hyp * 4);
+    alloc((void**)&r->d_offsets, (max_hyp + 1) * 4);
+    alloc((void**)&r->d_overflow, 256);
+    alloc((void**)&r->d_results, max_hyp * sizeof(pr_registration_result));
+    alloc(&r->ws_render, r->ws_render_bytes);
+    alloc(&r->ws_cloud, r->ws_cloud_bytes);
+    alloc(&r->ws_icp, r->ws_icp_bytes);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&r->h_overflow, 256);
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_tris, tris_host, n_tris * 36, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(r->d_overflow, 0, 256);
+    if (e != cudaSuccess) { pr_refiner_destroy(r); return (int)e; }
+    *out = r;
+    return PR_OK;
+}
+
+void pr_refiner_destroy(pr_refiner* r) {
+    if (!r) return;
+    free_scene(r);
+    cudaFree(r->d_tris); cudaFree(r->d_poses); cudaFree(r->d_depth); cudaFree(r->d_pts);
+    cudaFree(r->d_counts); cudaFree(r->d_offsets); cudaFree(r->d_overflow); cudaFree(r->d_results);
+    cudaFree(r->ws_render); cudaFree(r->ws_cloud); cudaFree(r->ws_icp);
+    if (r->h_overflow) cudaFreeHost(r->h_overflow);
+    delete r;
+}
+
+int pr_refiner_set_scene_projective(pr_refiner* r, const void* depth_host, int depth_is_int32, float max_dist_diff) {
+    if (!r || !depth_host) return PR_ERR_INVALID_ARGUMENT;
+    free_scene(r);
+    const size_t n_px = (size_t)r->W * r->H;
+    void* d_depth = nullptr;
+    PR_CUDA_TRY(cudaMalloc(&d_depth, n_px * (depth_is_int32 ? 4 : 2)));
+    cudaError_t e = cudaMalloc((void**)&r->d_scene_pcd, n_px * 12);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_scene_nrm, n_px * 12);
+    if (e == cudaSuccess) e = cudaMemcpy(d_depth, depth_host, n_px * (depth_is_int32 ? 4 : 2), cudaMemcpyHostToDevice);
+    int rc = (e == cudaSuccess) ? pr_scene_projective_init(d_depth, depth_is_int32, r->W, r->H, r->K, r->d_scene_pcd, r->d_scene_nrm, 0) : (int)e;
+    if (rc == PR_OK) { e = cudaDeviceSynchronize(); rc = (e == cudaSuccess) ? PR_OK : (int)e; }
+    cudaFree(d_depth);
+    if (rc != PR_OK) { free_scene(r); return rc; }
+    r->sp.width = r->W; r->sp.height = r->H; r->sp.max_dist_diff = max_dist_diff;
+    memcpy(r->sp.K, r->K, 36);
+    r->sp.pcd_dev = r->d_scene_pcd; r->sp.normal_dev = r->d_scene_nrm;
+    r->scene_kind = 0;
+    return PR_OK;
+}
+
+int pr_refiner_set_scene_nn(pr_refiner* r, const void* depth_host, int depth_is_int32) {
+    if (!r || !depth_host) return PR_ERR_INVALID_ARGUMENT;
+    free_scene(r);
+    const size_t n_px = (size_t)r->W * r->H;
+    std::vector<float> pcd(n_px * 3), nrm(n_px * 3);
+    std::vector<pr_node_kdtree> nodes(2 * n_px + 1);
+    size_t n_pts = 0, n_nodes = 0;
+    int rc = pr_scene_nn_build_host(depth_host, depth_is_int32, r->W, r->H, r->K, 10, pcd.data(), nrm.data(), n_px,
+                                    nodes.data(), nodes.size(), &n_pts, &n_nodes);
+    if (rc != PR_OK) return rc;
+    cudaError_t e = cudaMalloc((void**)&r->d_scene_pcd, n_pts * 12 + 256);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_scene_nrm, n_pts * 12 + 256);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_nodes, n_nodes * sizeof(pr_node_kdtree) + 256);
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_scene_pcd, pcd.data(), n_pts * 12, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_scene_nrm, nrm.data(), n_pts * 12, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_nodes, nodes.data(), n_nodes * sizeof(pr_node_kdtree), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { free_scene(r); return (int)e; }
+    r->sn.max_dist_diff = 0.1f;   // Scene_nn has no setter upstream (pcd_scene.h:49)
+    r->sn.pcd_dev = r->d_scene_pcd; r->sn.normal_dev = r->d_scene_nrm; r->sn.nodes_dev = r->d_nodes;
+    r->sn.n_points = n_pts; r->sn.n_nodes = n_nodes;
+    r->scene_kind = 1;
+    return PR_OK;
+}
+
+int pr_refiner_run_device(pr_refiner* r, const float* poses_dev, size_t n_hyp, pr_icp_criteria criteria,
+                          pr_registration_result* results_dev, pr_stream_t stream) {
+    if (!r || !poses_dev || !results_dev || n_hyp > r->max_hyp || r->scene_kind < 0) return PR_ERR_INVALID_ARGUMENT;
+    if (n_hyp == 0) return PR_OK;
+    return run_device(r, poses_dev, n_hyp, criteria, results_dev, prb::as_stream(stream));
+}
+
+int pr_refiner_run(pr_refiner* r, const float* poses_host, size_t n_hyp, pr_icp_criteria criteria,
+                   pr_registration_result* results_host, pr_stream_t stream_) {
+    if (!r || !poses_host || !results_host || n_hyp > r->max_hyp || r->scene_kind < 0) return PR_ERR_INVALID_ARGUMENT;
+    if (n_hyp == 0) return PR_OK;
+    cudaStream_t stream = prb::as_stream(stream_);
+    PR_CUDA_TRY(cudaMemcpyAsync(r->d_poses, poses_host, n_hyp * 64, cudaMemcpyHostToDevice, stream));
+    int rc = run_device(r, r->d_poses, n_hyp, criteria, r->d_results, stream);
+    if (rc != PR_OK) return rc;
+    PR_CUDA_TRY(cudaMemcpyAsync(results_host, r->d_results, n_hyp * sizeof(pr_registration_result), cudaMemcpyDeviceToHost, stream));
+    PR_CUDA_TRY(cudaMemcpyAsync(r->h_overflow, r->d_overflow, 4, cudaMemcpyDeviceToHost, stream));
+    PR_CUDA_TRY(cudaStreamSynchronize(stream));
+    return r->h_overflow[0] ? PR_ERR_CAPACITY : PR_OK;
+}
+
+int pr_refiner_buffers(pr_refiner* r, const int32_t** depth_dev, const float** pts_dev,
+                       const uint32_t** offsets_dev, const uint32_t** counts_dev) {
+    if (!r) return PR_ERR_INVALID_ARGUMENT;
+    if (depth_dev) *depth_dev = r->d_depth;
+    if (pts_dev) *pts_dev = r->d_pts;
+    if (offsets_dev) *offsets_dev = r->d_offsets;
+    if (counts_dev) *counts_dev = r->d_counts;
+    return PR_OK;
+}
+
+}  // extern "C"

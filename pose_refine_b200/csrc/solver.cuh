@@ -1,0 +1,83 @@
+// solver.cuh -- the 6x6 damped normal-equation solve and pose update, host + device.
+//
+// Replaces eigen_slover_666 + TransformVector6dToMatrix4d (cuda_icp/icp.cpp:7-45), which the
+// reference calls on the HOST from inside its CUDA iteration loop (icp.cu:207) -- the round trip
+// that makes its loop latency-bound.  Here the same arithmetic runs on one device thread of the
+// CTA that finishes a hypothesis' reduction.
+//
+// Arithmetic (all in double, cast to float at the end, as upstream):
+//   (A + 0.01 I) x = b   by LDL^T with symmetric diagonal pivoting (Eigen's LDLT algorithm:
+//   unblocked lower variant; the solve guards zero pivots), then
+//   R = Rz(x2) Ry(x1) Rx(x0) composed through unit quaternions (Eigen's AngleAxis product ->
+//   Quaternion::toRotationMatrix), t = (x3, x4, x5).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <float.h>
+
+namespace prb {
+
+template <class T> __host__ __device__ __forceinline__ void swap_vals(T& a, T& b) { T t = a; a = b; b = t; }
+
+// A: 6x6 symmetric (any of row/column-major), b: 6.  E: row-major 4x4 (16 floats).
+__host__ __device__ inline void solve_666(const float* A, const float* b, float* E) {
+    const int n = 6;
+    double a[6][6], x[6], tmp[6];
+    int tr[6];
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j < n; j++) a[i][j] = (double)A[i + 6 * j] + (i == j ? 0.01 : 0.0);
+        x[i] = (double)b[i];
+    }
+    for (int k = 0; k < n; k++) {
+        int piv = k;
+        double big = fabs(a[k][k]);
+        for (int i = k + 1; i < n; i++) if (fabs(a[i][i]) > big) { big = fabs(a[i][i]); piv = i; }
+        tr[k] = piv;
+        if (piv != k) {
+            for (int j = 0; j < k; j++) swap_vals(a[k][j], a[piv][j]);
+            for (int i = piv + 1; i < n; i++) swap_vals(a[i][k], a[i][piv]);
+            swap_vals(a[k][k], a[piv][piv]);
+            for (int i = k + 1; i < piv; i++) swap_vals(a[i][k], a[piv][i]);
+        }
+        if (k > 0) {
+            for (int j = 0; j < k; j++) tmp[j] = a[j][j] * a[k][j];
+            double acc = 0.0;
+            for (int j = 0; j < k; j++) acc += a[k][j] * tmp[j];
+            a[k][k] -= acc;
+            for (int i = k + 1; i < n; i++) {
+                double acc2 = 0.0;
+                for (int j = 0; j < k; j++) acc2 += a[i][j] * tmp[j];
+                a[i][k] -= acc2;
+            }
+        }
+        if (k + 1 < n && fabs(a[k][k]) > 0.0)
+            for (int i = k + 1; i < n; i++) a[i][k] /= a[k][k];
+    }
+    for (int k = 0; k < n; k++) if (tr[k] != k) swap_vals(x[k], x[tr[k]]);
+    for (int i = 0; i < n; i++) for (int j = 0; j < i; j++) x[i] -= a[i][j] * x[j];
+    for (int i = 0; i < n; i++) { if (fabs(a[i][i]) > DBL_MIN) x[i] /= a[i][i]; else x[i] = 0.0; }
+    for (int i = n - 1; i >= 0; i--) for (int j = i + 1; j < n; j++) x[i] -= a[j][i] * x[j];
+    for (int k = n - 1; k >= 0; k--) if (tr[k] != k) swap_vals(x[k], x[tr[k]]);
+
+    // q = qz * qy * qx with q_axis(angle) = (cos(angle/2), sin(angle/2) * axis)
+    const double cz = cos(0.5 * x[2]), sz = sin(0.5 * x[2]);
+    const double cy = cos(0.5 * x[1]), sy = sin(0.5 * x[1]);
+    const double cx = cos(0.5 * x[0]), sx = sin(0.5 * x[0]);
+    // qz*qy (Hamilton product with the structural zeros kept as exact 0 terms dropped)
+    const double aw = cz * cy, ax = -(sz * sy), ay = cz * sy, az = sz * cy;
+    // (qz*qy) * qx, qx = (cx, sx, 0, 0)
+    const double qw = aw * cx - ax * sx;
+    const double qx = aw * sx + ax * cx;
+    const double qy = ay * cx + az * sx;
+    const double qz = az * cx - ay * sx;
+    const double tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
+    const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
+    const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
+    const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+    E[0] = (float)(1.0 - (tyy + tzz)); E[1] = (float)(txy - twz); E[2] = (float)(txz + twy); E[3] = (float)x[3];
+    E[4] = (float)(txy + twz); E[5] = (float)(1.0 - (txx + tzz)); E[6] = (float)(tyz - twx); E[7] = (float)x[4];
+    E[8] = (float)(txz - twy); E[9] = (float)(tyz + twx); E[10] = (float)(1.0 - (txx + tyy)); E[11] = (float)x[5];
+    E[12] = 0.f; E[13] = 0.f; E[14] = 0.f; E[15] = 1.f;
+}
+
+}  // namespace prb
