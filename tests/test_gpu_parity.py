@@ -1,0 +1,378 @@
+"""GPU parity tests: every call goes through the C ABI (via pose_refine_b200.api) and is compared
+with the CPU oracle on the same inputs, and with the committed golden vectors.
+
+Bars (BASELINE.json north_star):
+  * integer / index work (rendered depth, cloud order, kd-tree, counts): bit-exact;
+  * float work that is a pure per-element map (depth2cloud, dep2pcd, normals): bit-exact;
+  * ICP (a float reduction whose summation order differs from the CPU's): final 4x4 within
+    1e-4 relative -- max|T_gpu - T_ref| <= 1e-4 * max|T_ref| (north_star's tolerance).  inlier_rmse_ and
+    fitness_ are functions of the DISCRETE inlier set (a model point a few 1e-8 m from a pixel boundary
+    or from the 0.1 m gate flips with any change of rounding), so they are held to 5e-3 relative (a transform change of 1e-4 alone shifts rmse by ~1%).
+"""
+import numpy as np
+import pytest
+
+from conftest import crc
+from pose_refine_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-4   # north_star: "within 1e-4 relative on the final 4x4 transform"
+STAT_TOL = 5e-3  # inlier_rmse_ / fitness_: a 1e-4 transform perturbation (allowed) moves a point 0.3 m from the origin by 30 um ~ 1% of a 2.6 mm rmse
+
+
+@pytest.fixture(scope="module")
+def api():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from pose_refine_b200 import api as a
+    return a
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    return torch
+
+
+def assert_result_close(got18, ref18, what=""):
+    got18, ref18 = np.asarray(got18, np.float64), np.asarray(ref18, np.float64)
+    Tg, Tr = got18[:16], ref18[:16]
+    err = np.abs(Tg - Tr).max()
+    assert err <= REL_TOL * np.abs(Tr).max(), f"{what}: transform differs by {err:.3e}\n{Tg.reshape(4,4)}\n{Tr.reshape(4,4)}"
+    assert abs(got18[16] - ref18[16]) <= STAT_TOL * max(abs(ref18[16]), 1e-12), f"{what}: rmse {got18[16]} vs {ref18[16]}"
+    assert abs(got18[17] - ref18[17]) <= STAT_TOL * max(abs(ref18[17]), 1e-12), f"{what}: fitness {got18[17]} vs {ref18[17]}"
+
+
+# ---------------------------------------------------------------------------------------------
+# rasteriser
+@pytest.mark.parametrize("use_tiles", [True, False])
+def test_render_fixture_bit_exact(api, mesh, golden, fixture_scene, use_tiles):
+    arrays, scal = golden
+    d = api.render_cuda_keep_in_gpu(mesh, arrays["poses"], 640, 480, arrays["proj"], use_tiles=use_tiles).cpu().numpy()
+    assert np.array_equal(d, fixture_scene["depth"])
+    assert [crc(x) for x in d] == [g["crc"] for g in scal["render"]]
+    d = api.render_cuda_keep_in_gpu(mesh, arrays["poses"], 640, 480, arrays["proj"], wl.ROI_FIXTURE, use_tiles=use_tiles).cpu().numpy()
+    assert d.shape == (2, 240, 320) and [crc(x) for x in d] == [g["crc"] for g in scal["render_roi"]]
+    d = api.render_cuda_keep_in_gpu(mesh, arrays["hyp8"], 640, 480, arrays["proj"], use_tiles=use_tiles).cpu().numpy()
+    assert [crc(x) for x in d] == [g["crc"] for g in scal["render_hyp8"]]
+
+
+@pytest.mark.parametrize("use_tiles", [True, False])
+def test_render_odd_sizes_roi_and_near_plane(api, mesh, golden, use_tiles):
+    arrays, scal = golden
+    d = api.render_cuda_keep_in_gpu(mesh, arrays["poses"], 161, 121, arrays["proj_small"], use_tiles=use_tiles).cpu().numpy()
+    assert [crc(x) for x in d] == [g["crc"] for g in scal["render_small"]]
+    d = api.render_cuda_keep_in_gpu(mesh, arrays["poses"], 161, 121, arrays["proj_small"], (33, 17, 71, 53), use_tiles=use_tiles).cpu().numpy()
+    assert [crc(x) for x in d] == [g["crc"] for g in scal["render_small_roi"]]
+    d = api.render_cuda_keep_in_gpu(mesh, arrays["pose_near"][None], 640, 480, arrays["proj"], use_tiles=use_tiles).cpu().numpy()
+    assert crc(d[0]) == scal["render_near"]["crc"] and int(d.min()) == scal["render_near"]["min"]
+
+
+def test_render_wrappers_agree_like_reference_test(api, mesh, golden, torch_mod):
+    """cuda_renderer/test.cpp:94-106: render_cuda == render_cuda_keep_in_gpu == render_cpu for 100 equal poses
+    (10 here), host poses vs device poses, host tris vs device tris."""
+    arrays, scal = golden
+    poses = np.repeat(arrays["poses"][:1], 10, axis=0)
+    host = api.render_cuda(mesh, poses, 640, 480, arrays["proj"])
+    tris_dev = torch_mod.as_tensor(mesh).cuda()
+    keep = api.render_cuda_keep_in_gpu(tris_dev, torch_mod.as_tensor(poses).cuda(), 640, 480, arrays["proj"])
+    assert np.abs(host - keep.cpu().numpy()).sum() == 0
+    assert all(crc(x) == scal["render"][0]["crc"] for x in host)
+
+
+def test_render_sphere_behind_camera_and_empty(api, port, golden):
+    arrays, _ = golden
+    tris = wl.uv_sphere(50.0, 40, 37)
+    poses = wl.shoemake_poses(3, seed=5)
+    poses[2, 2, 3] = 30.0
+    want = port.render(tris, poses, 640, 480, arrays["proj"])
+    for use_tiles in (True, False):
+        got = api.render_cuda_keep_in_gpu(tris, poses, 640, 480, arrays["proj"], use_tiles=use_tiles).cpu().numpy()
+        assert np.array_equal(got, want)
+    # object completely outside the frame -> all zeros; zero poses -> empty tensor
+    far = wl.pose44(np.eye(3, dtype=np.float32), [5000.0, 0.0, 300.0])[None]
+    assert int(api.render_cuda_keep_in_gpu(tris, far, 640, 480, arrays["proj"]).abs().sum()) == 0
+    assert api.render_cuda_keep_in_gpu(tris, np.zeros((0, 4, 4), np.float32), 640, 480, arrays["proj"]).shape[0] == 0
+
+
+def test_render_big_triangles_overflowing_bins(api, port, golden):
+    """A few screen-filling triangles: every tile lists them; the per-pose list capacity still holds,
+    and with a deliberately tiny workspace the overflow fallback must give the same image."""
+    import ctypes as C
+    import torch
+    from pose_refine_b200 import _lib
+    arrays, _ = golden
+    rng = np.random.RandomState(1)
+    tris = (rng.uniform(-400, 400, size=(300, 9))).astype(np.float32)
+    tris[:, 2::3] = rng.uniform(-20, 20, size=(300, 3))
+    poses = wl.hypotheses(3, seed=3)
+    want = port.render(tris, poses, 640, 480, arrays["proj"])
+    got = api.render_cuda_keep_in_gpu(tris, poses, 640, 480, arrays["proj"]).cpu().numpy()
+    assert np.array_equal(got, want)
+    # tiny list capacity (1024 ids per pose) -> overflow flag -> tiles scan all triangles
+    L = _lib.lib()
+    fixed = L.pr_render_workspace_bytes(3, 0, 640, 480) - 3 * 1024 * 4
+    ws_bytes = fixed + 3 * 1024 * 4 + 64
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    out = torch.empty((3, 480, 640), dtype=torch.int32, device="cuda")
+    t = torch.as_tensor(tris).cuda()
+    p = torch.as_tensor(poses.reshape(-1, 16)).cuda()
+    proj = np.ascontiguousarray(arrays["proj"], np.float32)
+    rc = L.pr_render_batch(t.data_ptr(), 300, p.data_ptr(), 1, 3, 640, 480, proj.ctypes.data, _lib.Roi(0, 0, 0, 0),
+                           out.data_ptr(), ws.data_ptr(), ws_bytes, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_raw2depth_mask(api, port, fixture_scene, torch_mod):
+    raw = fixture_scene["depth"].copy()
+    raw[0, 0, :4] = [70000, -5, 65536, 1]
+    d, m = api.raw2depth_mask_cuda(raw)
+    wd, wm = port.raw2depth_mask(raw)
+    assert np.array_equal(d.cpu().numpy(), wd) and np.array_equal(m.cpu().numpy(), wm)
+    assert np.array_equal(api.raw2depth_uint16_cuda(raw).cpu().numpy(), wd)
+    assert np.array_equal(api.raw2mask_uint8_cuda(raw).cpu().numpy(), wm)
+
+
+# ---------------------------------------------------------------------------------------------
+# depth2cloud
+def test_depth2cloud_bit_exact(api, port, mesh, golden, torch_mod):
+    arrays, scal = golden
+    K = arrays["K"]
+    depth = port.render(mesh, arrays["hyp8"], 640, 480, arrays["proj"])
+    depth[3] = 0                      # an empty image in the middle of the batch
+    dd = torch_mod.as_tensor(depth).cuda()
+    for align in (1, 4):
+        pts, offsets, counts = api.depth2cloud_batch(dd, K, align_points=align)
+        pts, offsets, counts = pts.cpu().numpy(), offsets.cpu().numpy(), counts.cpu().numpy()
+        assert counts[3] == 0 and all(o % align == 0 for o in offsets)
+        for i in range(8):
+            want = port.depth2cloud(depth[i], K)
+            assert counts[i] == len(want)
+            assert np.array_equal(pts[offsets[i]: offsets[i] + counts[i]], want)
+    # uint16 input, ROI-cropped image with tl offsets, odd-sized image (scalar load path)
+    u16 = torch_mod.as_tensor(depth[0].astype(np.uint16)).cuda()
+    assert np.array_equal(api.depth2cloud_cuda(u16, 640, 480, K).cpu().numpy(), port.depth2cloud(depth[0].astype(np.uint16), K))
+    roi = wl.ROI_FIXTURE
+    droi = np.ascontiguousarray(depth[0][roi[1]: roi[1] + roi[3], roi[0]: roi[0] + roi[2]])
+    got = api.depth2cloud_cuda(torch_mod.as_tensor(droi).cuda(), roi[2], roi[3], K, 1, roi[0], roi[1]).cpu().numpy()
+    assert np.array_equal(got, port.depth2cloud(droi, K, 1, roi[0], roi[1]))
+    odd = np.ascontiguousarray(depth[1][:121, :161])
+    assert np.array_equal(api.depth2cloud_cuda(torch_mod.as_tensor(odd).cuda(), 161, 121, K).cpu().numpy(), port.depth2cloud(odd, K))
+    got = api.depth2cloud_cuda(torch_mod.as_tensor(depth[0]).cuda(), 640, 480, K).cpu().numpy()
+    assert len(got) == arrays["hyp8_counts"][0]
+
+
+def test_depth2cloud_stride_rejected(api, torch_mod, golden):
+    from pose_refine_b200._lib import PoseRefineError
+    d = torch_mod.zeros((1, 480, 640), dtype=torch_mod.int32, device="cuda")
+    with pytest.raises(PoseRefineError):
+        api.depth2cloud_batch(d, golden[0]["K"], stride=2)
+
+
+# ---------------------------------------------------------------------------------------------
+# scenes
+def test_scene_projective_init_bit_exact(api, port, fixture_scene, golden):
+    arrays, scal = golden
+    K = arrays["K"]
+    for depth in (fixture_scene["scene_depth"], fixture_scene["scene_depth"].astype(np.uint16),
+                  wl.plane_scene_depth(fixture_scene["scene_depth"], target_valid=60000)):
+        s = api.SceneProjective().init_cuda(depth, K)
+        want_pcd, want_nrm, _ = port.scene_projective(depth, K).arrays()
+        assert np.array_equal(s.pcd.cpu().numpy(), want_pcd)
+        assert np.array_equal(s.normal.cpu().numpy(), want_nrm)
+    s = api.SceneProjective().init_cuda(fixture_scene["scene_depth"], K)
+    assert crc(s.pcd.cpu().numpy()) == scal["scene_projective"]["pcd_crc"]
+    assert crc(s.normal.cpu().numpy()) == scal["scene_projective"]["normal_crc"]
+
+
+def test_scene_nn_build_bit_exact(api, port, fixture_scene, golden):
+    arrays, scal = golden
+    K = arrays["K"]
+    s = api.SceneNN().init_cuda(fixture_scene["scene_depth"], K)
+    g = scal["scene_nn"]
+    assert (s.pcd.shape[0], len(s.nodes_host)) == (g["n_pts"], g["n_nodes"])
+    assert crc(s.pcd.cpu().numpy()) == g["pcd_crc"] and crc(s.normal.cpu().numpy()) == g["normal_crc"]
+    assert crc(s.nodes_host) == g["nodes_crc"]
+    comp = wl.plane_scene_depth(fixture_scene["scene_depth"], target_valid=50000)
+    s = api.SceneNN().init_cuda(comp, K)
+    wp, wn, wnodes = port.scene_nn(comp, K).arrays()
+    assert np.array_equal(s.pcd.cpu().numpy(), wp) and np.array_equal(s.normal.cpu().numpy(), wn)
+    assert s.nodes_host.tobytes() == wnodes.tobytes()
+
+
+# ---------------------------------------------------------------------------------------------
+# ICP pieces
+def _terms_f64(p, q, n, valid):
+    """per-point thrust__pcd2Ab terms (icp.h:138-208) in float64 from the oracle's correspondences"""
+    p, q, n = p[valid].astype(np.float64), q[valid].astype(np.float64), n[valid].astype(np.float64)
+    d = q - p
+    r = (d * n).sum(1)
+    J = np.concatenate([np.cross(p, n), n], axis=1)
+    cols = [J[:, i] * J[:, j] for i in range(6) for j in range(i, 6)] + [J[:, i] * r for i in range(6)]
+    cols += [(d * d).sum(1), np.ones(len(p))]
+    return np.stack(cols, axis=1)
+
+
+def test_pcd2ab_matches_oracle(api, port, fixture_scene, golden):
+    """One reduction pass.  Ground truth = float64 sum of the per-point terms built from the ORACLE's
+    correspondences; the GPU float32 result must be within 2e-6 of sum|term| of it (the CPU's own
+    sequential float32 sum is no closer), the inlier count must be exact."""
+    arrays, _ = golden
+    K, cloud = arrays["K"], fixture_scene["cloud"]
+    sp = api.SceneProjective().init_cuda(fixture_scene["scene_depth"], K)
+    sn = api.SceneNN().init_cuda(fixture_scene["scene_depth"], K)
+    for scene, pscene, key in ((sp, port.scene_projective(fixture_scene["scene_depth"], K), "pcd2ab_projective"),
+                               (sn, port.scene_nn(fixture_scene["scene_depth"], K), "pcd2ab_nn")):
+        got = api.pcd2ab(cloud, scene).astype(np.float64)
+        q, n, valid = port.query(pscene, cloud)
+        terms = _terms_f64(cloud, q, n, valid)
+        truth, mag = terms.sum(0), np.abs(terms).sum(0)
+        assert got[28] == truth[28] == arrays[key][28], "valid-correspondence count must be exact"
+        assert np.all(np.abs(got - truth) <= 2e-6 * mag), (got - truth) / mag
+        assert np.all(np.abs(arrays[key].astype(np.float64) - truth) <= 2e-5 * mag), "golden CPU sums are themselves only this close"
+
+
+def test_icp_projective_fixture(api, port, fixture_scene, golden, torch_mod):
+    arrays, _ = golden
+    K = arrays["K"]
+    sp = api.SceneProjective().init_cuda(fixture_scene["scene_depth"], K)
+    for key, crit in (("icp_projective_fixed30", (0.0, 0.0, 30)), ("icp_projective_fixed3", (0.0, 0.0, 3))):
+        model = torch_mod.as_tensor(fixture_scene["cloud"]).cuda()
+        r = api.ICP_Point2Plane_cuda(model, sp, api.ICPConvergenceCriteria(*crit))
+        got = np.concatenate([r.transformation_.reshape(-1), [r.inlier_rmse_, r.fitness_]])
+        assert_result_close(got, arrays[key], key)
+        # the model cloud is transformed in place, like upstream (test.cpp:129 comment)
+        want_pts = port.icp(port.scene_projective(fixture_scene["scene_depth"], K), fixture_scene["cloud"], *crit)["pts"]
+        assert np.abs(model.cpu().numpy() - want_pts).max() < 2e-5
+
+
+def test_icp_default_criteria_matches_at_matched_iteration(api, port, fixture_scene, golden, torch_mod):
+    """With early exit the pass count depends on float summation order: the GPU
+    result must equal the oracle's at the oracle's own stopping pass or one pass either side."""
+    arrays, _ = golden
+    K = arrays["K"]
+    for mk_api, mk_port in ((api.SceneProjective, "scene_projective"), (api.SceneNN, "scene_nn")):
+        scene = mk_api().init_cuda(fixture_scene["scene_depth"], K)
+        pscene = getattr(port, mk_port)(fixture_scene["scene_depth"], K)
+        port.set_threads(8)
+        k0 = port.icp(pscene, fixture_scene["cloud"])["last_pass"]
+        cands = [port.icp(pscene, fixture_scene["cloud"], 0.0, 0.0, k)["raw"] for k in (k0 - 1, k0, k0 + 1)]
+        port.set_threads(1)
+        model = torch_mod.as_tensor(fixture_scene["cloud"]).cuda()
+        r = api.ICP_Point2Plane_cuda(model, scene)
+        got = np.concatenate([r.transformation_.reshape(-1), [r.inlier_rmse_, r.fitness_]])
+        errs = [np.abs(got[:16] - c[:16]).max() for c in cands]
+        assert min(errs) <= REL_TOL, (mk_port, k0, errs)
+
+
+def test_icp_nn_fixture(api, fixture_scene, golden, torch_mod):
+    arrays, _ = golden
+    sn = api.SceneNN().init_cuda(fixture_scene["scene_depth"], arrays["K"])
+    model = torch_mod.as_tensor(fixture_scene["cloud"]).cuda()
+    r = api.ICP_Point2Plane_cuda(model, sn, api.ICPConvergenceCriteria(0.0, 0.0, 30))
+    got = np.concatenate([r.transformation_.reshape(-1), [r.inlier_rmse_, r.fitness_]])
+    assert_result_close(got, arrays["icp_nn_fixed30"], "icp_nn_fixed30")
+
+
+def test_icp_batch_hyp8_and_ragged_edge_cases(api, port, mesh, fixture_scene, golden, torch_mod):
+    arrays, _ = golden
+    K = arrays["K"]
+    sp = api.SceneProjective().init_cuda(fixture_scene["scene_depth"], K)
+    depth = api.render_cuda_keep_in_gpu(mesh, arrays["hyp8"], 640, 480, arrays["proj"])
+    pts, offsets, counts = api.depth2cloud_batch(depth, K)
+    assert np.array_equal(counts.cpu().numpy(), arrays["hyp8_counts"])
+    crit = api.ICPConvergenceCriteria(0.0, 0.0, 30)
+    res = api.icp_batch(pts, offsets, counts, sp, crit).cpu().numpy()
+    for i in range(8):
+        assert_result_close(res[i], arrays["icp_hyp8_projective_fixed30"][i], f"hyp {i}")
+    # same hypotheses, different batch composition: empty cloud + non-overlapping cloud + a permutation.
+    # Summation order is fixed per hypothesis, so results are bit-identical whatever the batch looks like.
+    h_pts, h_off, h_cnt = pts.cpu().numpy(), offsets.cpu().numpy(), counts.cpu().numpy()
+    clouds = [h_pts[h_off[i]: h_off[i] + h_cnt[i]] for i in range(8)]
+    mix = [clouds[5], np.zeros((0, 3), np.float32), clouds[0], np.tile(np.array([[5.0, 5.0, 1.0]], np.float32), (33, 1)), clouds[7][:1000]]
+    cat = np.concatenate(mix)
+    off = np.cumsum([0] + [len(c) for c in mix]).astype(np.int32)
+    res2 = api.icp_batch(torch_mod.as_tensor(cat).cuda(), torch_mod.as_tensor(off[:-1]).cuda(),
+                         torch_mod.as_tensor(np.array([len(c) for c in mix], np.int32)).cuda(), sp, crit).cpu().numpy()
+    assert np.array_equal(res2[0], res[5]) and np.array_equal(res2[2], res[0])
+    ident = np.concatenate([np.eye(4, dtype=np.float32).reshape(-1), [0, 0]])
+    assert np.array_equal(res2[1], ident) and np.array_equal(res2[3], ident)     # count == 0 on the first pass (icp.cu:183)
+    want = port.icp(port.scene_projective(fixture_scene["scene_depth"], K), mix[4], 0.0, 0.0, 30)["raw"]
+    assert_result_close(res2[4], want, "truncated cloud")
+    # max_iteration = 0: one evaluation pass only
+    r0 = api.icp_batch(pts, offsets, counts, sp, api.ICPConvergenceCriteria(0.0, 0.0, 0)).cpu().numpy()
+    assert np.array_equal(r0[:, :16], np.tile(np.eye(4, dtype=np.float32).reshape(-1), (8, 1)))
+    want0 = port.icp(port.scene_projective(fixture_scene["scene_depth"], K), clouds[0], 0.0, 0.0, 0)["raw"]
+    assert_result_close(r0[0], want0, "max_iteration=0")
+
+
+# ---------------------------------------------------------------------------------------------
+# the whole path behind one call, host buffers in / out
+def test_refiner_end_to_end(api, port, mesh, fixture_scene, golden):
+    arrays, _ = golden
+    K = arrays["K"]
+    ref = api.PoseRefiner(mesh, 640, 480, K, max_hyp=16)
+    ref.set_scene_projective(fixture_scene["scene_depth"])
+    res = ref.run(arrays["hyp8"], api.ICPConvergenceCriteria(0.0, 0.0, 30))
+    for i in range(8):
+        assert_result_close(res[i], arrays["icp_hyp8_projective_fixed30"][i], f"refiner hyp {i}")
+    depth, pts, offsets, counts = ref.buffers(8)
+    assert np.array_equal(counts.cpu().numpy(), arrays["hyp8_counts"])
+    assert [crc(x) for x in depth.cpu().numpy()] == [g["crc"] for g in golden[1]["render_hyp8"]]
+    # nearest-neighbour scene through the same object, two hypotheses
+    ref.set_scene_nn(fixture_scene["scene_depth"])
+    crit = (0.0, 0.0, 30)
+    res = ref.run(arrays["hyp8"][:2], api.ICPConvergenceCriteria(*crit))
+    pn = port.scene_nn(fixture_scene["scene_depth"], K)
+    port.set_threads(8)
+    _, want, _ = port.pipeline(pn, mesh, arrays["hyp8"][:2], 640, 480, arrays["proj"], K, *crit, schedule=0)
+    port.set_threads(1)
+    for i in range(2):
+        assert_result_close(res[i], want[i], f"refiner nn hyp {i}")
+    ref.close()
+
+
+def test_refiner_capacity_overflow_is_reported(api, mesh, fixture_scene, golden):
+    from pose_refine_b200._lib import PoseRefineError
+    arrays, _ = golden
+    ref = api.PoseRefiner(mesh, 640, 480, arrays["K"], max_hyp=8, capacity_points=60000)   # room for ~2 clouds
+    ref.set_scene_projective(fixture_scene["scene_depth"])
+    with pytest.raises(PoseRefineError) as e:
+        ref.run(arrays["hyp8"], api.ICPConvergenceCriteria(0.0, 0.0, 2))
+    assert e.value.status == -4
+    ref.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json config C2: 512 hypotheses, 640x480)
+def test_full_size_properties(api, port, mesh, fixture_scene, golden, torch_mod):
+    arrays, _ = golden
+    K = arrays["K"]
+    P = 512
+    poses = wl.hypotheses(P, seed=1234)
+    a = api.render_cuda_keep_in_gpu(mesh, poses, 640, 480, arrays["proj"], use_tiles=True)
+    b = api.render_cuda_keep_in_gpu(mesh, poses, 640, 480, arrays["proj"], use_tiles=False)
+    assert torch_mod.equal(a, b), "tile path and global-atomic path must render identical images"
+    assert torch_mod.equal(a, api.render_cuda_keep_in_gpu(mesh, poses, 640, 480, arrays["proj"])), "render must be deterministic"
+    pts, offsets, counts = api.depth2cloud_batch(a, K)
+    assert torch_mod.equal(counts.long(), (a > 0).flatten(1).sum(1)), "cloud size == number of valid pixels"
+    z = pts[:, 2]
+    assert float(z.max()) < 0.5 and int(offsets[P]) >= int(counts.sum())
+    sp = api.SceneProjective().init_cuda(fixture_scene["scene_depth"], K)
+    crit = api.ICPConvergenceCriteria(0.0, 0.0, 30)
+    res = api.icp_batch(pts, offsets, counts, sp, crit)
+    assert torch_mod.equal(res, api.icp_batch(pts, offsets, counts, sp, crit)), "ICP must be deterministic"
+    r = res.cpu().numpy()
+    R = r[:, :16].reshape(P, 4, 4)[:, :3, :3].astype(np.float64)
+    assert np.abs(R @ R.transpose(0, 2, 1) - np.eye(3)).max() < 1e-4, "accumulated updates stay rotations"
+    assert np.isfinite(r).all() and (r[:, 17] >= 0).all() and (r[:, 17] <= 1).all() and (r[:, 17] > 0.5).mean() > 0.7
+    # spot-check hypotheses against the oracle end to end
+    ps = port.scene_projective(fixture_scene["scene_depth"], K)
+    for i in (0, 137, 511):
+        d = port.render(mesh, poses[i: i + 1], 640, 480, arrays["proj"])[0]
+        assert np.array_equal(a[i].cpu().numpy(), d)
+        want = port.icp(ps, port.depth2cloud(d, K), 0.0, 0.0, 30)["raw"]
+        assert_result_close(r[i], want, f"hyp {i} of 512")
