@@ -181,13 +181,25 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32]) {
     return v[0];
 }
 
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+// Cross-CTA signalling inside the persistent kernel.  Everything a waiter reads after the signal
+// (HypState::T, the chunk partials) is read with ld.global.cg, i.e. from L2, and every producer
+// publishes with a gpu-scope RELEASE (its earlier stores are in L2 before the flag / ticket is
+// visible).  The waiter therefore polls with a RELAXED load: an acquire load would make ptxas add
+// CCTL.IVALL -- an invalidate of the SM's whole L1 -- to every poll, which evicts the scene lines
+// the other warps of the SM are gathering from (measured: L1 hit rate 10%, 17% of all stall samples
+// on CCTL.IVALL).  The dependent loads are issued only after the poll's branch resolves and bypass L1.
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned atom_add_release(unsigned* p, unsigned v) {
+    unsigned old;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
 }
 
 // The stop logic of one hypothesis after its sums S[29] are known (icp.cu:179-212), run by one
@@ -195,7 +207,7 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 // persistent driver's flavour: state is read past L1 and `pass` / `done` are published with release
 // stores after everything else, because other CTAs of the SAME launch are waiting on them.
 template <bool RELEASE>
-__device__ void finish_pass_impl(HypState* st, const float* S, unsigned n_points, pr_icp_criteria crit,
+__device__ __noinline__ void finish_pass_impl(HypState* st, const float* S, unsigned n_points, pr_icp_criteria crit,
                                  pr_registration_result* res) {
     const float count = S[28], total = S[27];
     const int iter = RELEASE ? __ldcg(&st->pass) : st->pass;
@@ -211,7 +223,8 @@ __device__ void finish_pass_impl(HypState* st, const float* S, unsigned n_points
         else if (fabsf(fitness - prev_fit) < crit.relative_fitness && fabsf(rmse - prev_rmse) < crit.relative_rmse)
             ret = true;                                        // icp.cu:191-194
     }
-    st->fitness = fitness; st->rmse = rmse;
+    if (RELEASE) { __stcg(&st->fitness, fitness); __stcg(&st->rmse, rmse); }
+    else { st->fitness = fitness; st->rmse = rmse; }
     float T[16];
 #pragma unroll
     for (int i = 0; i < 12; i++) T[i] = RELEASE ? __ldcg(&st->T[i]) : st->T[i];
@@ -237,14 +250,14 @@ __device__ void finish_pass_impl(HypState* st, const float* S, unsigned n_points
                 Tn[4 * i + j] = acc;
             }
 #pragma unroll
-        for (int i = 0; i < 12; i++) st->T[i] = Tn[i];
-        if (RELEASE) { __threadfence(); st_release(reinterpret_cast<unsigned*>(&st->pass), (unsigned)(iter + 1)); }
+        for (int i = 0; i < 12; i++) { if (RELEASE) __stcg(&st->T[i], Tn[i]); else st->T[i] = Tn[i]; }
+        if (RELEASE) st_release(reinterpret_cast<unsigned*>(&st->pass), (unsigned)(iter + 1));
         else st->pass = iter + 1;
     } else {
 #pragma unroll
         for (int i = 0; i < 16; i++) res->transformation[i] = T[i];
         res->inlier_rmse = rmse; res->fitness = fitness;
-        if (RELEASE) { __threadfence(); st_release(reinterpret_cast<unsigned*>(&st->done), 1u); }
+        if (RELEASE) st_release(reinterpret_cast<unsigned*>(&st->done), 1u);
         else st->done = 1;
     }
 }
@@ -385,11 +398,20 @@ icp_pass_kernel(const float* __restrict__ pts, const uint32_t* __restrict__ offs
 }
 
 // ---------------------------------------------------------------------------------------------
-// persistent driver
+// persistent driver: warps are independent workers
 // ---------------------------------------------------------------------------------------------
-constexpr int kTilePts = 2048;                 // points per shared-memory tile (24 KB)
-constexpr int kTileFloats = kTilePts * 3;
-constexpr uint32_t kPersistChunk = 8192;       // points per work item (4 tiles)
+// Every warp runs its own loop: claim a work item (pass, chunk of kPersistChunk points of one
+// hypothesis) from the global counter, stream the chunk through its own double-buffered
+// shared-memory tiles (TMA bulk copies issued by lane 0, completion on the warp's own mbarriers),
+// reduce its 29 sums with the transposing butterfly and deposit one partial per item.  There is no
+// CTA-wide barrier anywhere; the only cross-warp synchronisation is the per-hypothesis
+// acquire/release on HypState::pass / done and the ticket counter.
+constexpr int kWTile = 512;                    // points per warp tile (6 KB)
+constexpr int kWTileFloats = kWTile * 3;
+constexpr int kWTileBytes = kWTileFloats * 4;
+constexpr int kWStages = 2;
+constexpr uint32_t kPersistChunk = 2048;       // points per work item (4 tiles, 64 points per lane)
+constexpr int kPersistSmem = kIcpWarps * kWStages * kWTileBytes + kIcpWarps * kWStages * 8;
 
 struct IcpCtl {            // device-side control block
     unsigned next_item;    // work-item claim counter
@@ -402,7 +424,7 @@ struct PackedScene {
     int W, H;
     float fW, fH;
     float max_dist;
-    float fx, fy, cx, cy;
+    float fx, fy, cx05, cy05;     // cx + 0.5, cy + 0.5
     const float4* qn;
     const float2* n2;
 };
@@ -417,13 +439,13 @@ scene_pack_kernel(const float* __restrict__ pcd, const float* __restrict__ nrm, 
 }
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     unsigned done = 0;
     while (!done) {
         asm volatile(
@@ -431,53 +453,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
             ".reg .pred p;\n"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
             "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     }
 }
 // TMA bulk copy global -> shared (1-D), completion signalled on an mbarrier
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+__device__ __forceinline__ void tma_load_1d(unsigned smem_dst, const void* gmem_src, unsigned bytes, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+                 ::"r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
 }
-struct ItemDesc {
-    unsigned item, h, pass, n_h, n_pts, n_tiles;
-    const float* g;        // first point of the item
-    bool valid;
-};
-
-__device__ __forceinline__ ItemDesc describe_item(unsigned item, unsigned n_items, unsigned total, const float* pts,
-                                                  const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
-                                                  const uint32_t* __restrict__ chunk_hyp, const HypState* state) {
-    ItemDesc d;
-    d.item = item;
-    d.valid = item < n_items;
-    d.h = d.pass = d.n_h = d.n_pts = d.n_tiles = 0;
-    d.g = pts;
-    if (d.valid) {
-        d.pass = item / total;
-        const unsigned c = item - d.pass * total;
-        d.h = __ldg(chunk_hyp + c);
-        d.n_h = __ldg(counts + d.h);
-        const unsigned first = (c - __ldcg(&state[d.h].chunk_begin)) * kPersistChunk;
-        d.n_pts = min(kPersistChunk, d.n_h - first);
-        d.n_tiles = (d.n_pts + kTilePts - 1) / kTilePts;
-        d.g = pts + 3 * ((size_t)__ldg(offsets + d.h) + first);
-    }
-    return d;
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
 }
-
-// the four points a thread owns in a tile: floats [12g, 12g+12) -> three conflict-free LDS.128
-struct Quad { float x[4], y[4], z[4]; };
-__device__ __forceinline__ Quad load_quad(const float* tile, unsigned g) {
-    const float4 a = *reinterpret_cast<const float4*>(tile + 12 * g);
-    const float4 b = *reinterpret_cast<const float4*>(tile + 12 * g + 4);
-    const float4 c = *reinterpret_cast<const float4*>(tile + 12 * g + 8);
-    Quad q;
-    q.x[0] = a.x; q.y[0] = a.y; q.z[0] = a.z;
-    q.x[1] = a.w; q.y[1] = b.x; q.z[1] = b.y;
-    q.x[2] = b.z; q.y[2] = b.w; q.z[2] = c.x;
-    q.x[3] = c.y; q.y[3] = c.z; q.z[3] = c.w;
-    return q;
+__device__ __forceinline__ float lds32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(unsigned addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
 __device__ __forceinline__ void transform(const float* T, float x, float y, float z, float& px, float& py, float& pz) {
@@ -487,57 +482,121 @@ __device__ __forceinline__ void transform(const float* T, float x, float y, floa
     pz = fmaf(T[10], z, fmaf(T[9], y, fmaf(T[8], x, T[11])));
 }
 
-// one tile, packed projective scene: per thread two quads; the four gathers of a quad are issued
-// before any of them is consumed.
-__device__ __forceinline__ void compute_tile(const PackedScene& s, const float* tile, unsigned n, const float* T, float* acc) {
-#pragma unroll 1
-    for (unsigned g = threadIdx.x; 4 * g < n; g += kIcpThreads) {
-        const Quad q = load_quad(tile, g);
-        float px[4], py[4], pz[4];
-        int idx[4];
+// 1/z for the projection: hardware reciprocal + one Newton step (faithful to within 1 ulp for the
+// normal-range depths a point cloud holds); any other input still yields a value the bounds test
+// below classifies safely.
+__device__ __forceinline__ float fast_rcp(float z) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(z));
+    const float e = fmaf(-z, r, 1.0f);
+    return fmaf(r, e, r);
+}
+
+// 128 consecutive points of a tile against the packed projective scene: lane l owns points
+// l, 32+l, 64+l, 96+l, so each of the four gather instructions covers 32 CONSECUTIVE model points --
+// neighbouring scene pixels, i.e. 4 cache lines per 128-bit gather instead of 16.  The four gathers
+// are issued before any of them is consumed.
+// Pixel selection: u = int(px/pz*fx + cx + 0.5) (common.h:63-73) evaluated as
+// fma(px*(1/pz), fx, cx+0.5), within 2 ulp of the reference's operation order.  "0 <= int(v) < W" is
+// tested on the truncated integers as unsigned compares; fmaxf(v, -2) first turns NaN into a
+// rejected value (a plain float->int conversion would turn NaN into pixel 0).
+template <bool TAIL>
+__device__ __forceinline__ void group_projective(const PackedScene& s, unsigned addr, unsigned first, unsigned n,
+                                                 const float* T, float* acc) {
+    float px[4], py[4], pz[4];
+    int idx[4];
+    bool ok[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            transform(T, q.x[k], q.y[k], q.z[k], px[k], py[k], pz[k]);
-            // Scene_projective::query pixel selection (depth_scene.h:30-36, common.h:63-73), exact ops
-            const float uf = addf(addf(mulf(divf(px[k], pz[k]), s.fx), s.cx), 0.5f);
-            const float vf = addf(addf(mulf(divf(py[k], pz[k]), s.fy), s.cy), 0.5f);
-            const bool in = (uf > -1.0f && uf < s.fW && vf > -1.0f && vf < s.fH) && (4 * g + k < n);
-            idx[k] = in ? ((int)uf + (int)vf * s.W) : -1;
+    for (int k = 0; k < 4; k++) {
+        const float x = lds32(addr + 384 * k), y = lds32(addr + 384 * k + 4), z = lds32(addr + 384 * k + 8);
+        transform(T, x, y, z, px[k], py[k], pz[k]);
+        const float rz = fast_rcp(pz[k]);
+        const int ui = __float2int_rz(fmaxf(fmaf(px[k] * rz, s.fx, s.cx05), -2.0f));
+        const int vi = __float2int_rz(fmaxf(fmaf(py[k] * rz, s.fy, s.cy05), -2.0f));
+        ok[k] = ((unsigned)ui < (unsigned)s.W) & ((unsigned)vi < (unsigned)s.H);
+        if (TAIL) ok[k] = ok[k] & (first + 32 * k < n);
+        idx[k] = vi * s.W + ui;
+    }
+    float4 A[4];
+    float2 B[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (ok[k]) {
+            A[k] = __ldg(s.qn + idx[k]);
+            B[k] = __ldg(s.n2 + idx[k]);
         }
-        float4 A[4];
-        float2 B[4];
+    }
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (idx[k] >= 0) {
-                A[k] = __ldg(s.qn + idx[k]);
-                B[k] = __ldg(s.n2 + idx[k]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (idx[k] >= 0) {
-                const float dz = pz[k] - A[k].z;
-                const float adz = (dz > 0.f) ? dz : -dz;
-                if (!(A[k].z <= 0.f || adz > s.max_dist)) {       // depth_scene.h:42
-                    Corr c;
-                    c.qx = A[k].x; c.qy = A[k].y; c.qz = A[k].z; c.nx = A[k].w; c.ny = B[k].x; c.nz = B[k].y;
-                    accumulate(acc, px[k], py[k], pz[k], c);
-                }
+    for (int k = 0; k < 4; k++) {
+        if (ok[k]) {
+            if (A[k].z > 0.f && fabsf(pz[k] - A[k].z) <= s.max_dist) {       // depth_scene.h:42
+                Corr cr;
+                cr.qx = A[k].x; cr.qy = A[k].y; cr.qz = A[k].z; cr.nx = A[k].w; cr.ny = B[k].x; cr.nz = B[k].y;
+                accumulate(acc, px[k], py[k], pz[k], cr);
             }
         }
     }
 }
 
-// one tile, any scene with a per-point query() (nearest neighbour)
-template <class SceneT>
-__device__ __forceinline__ void compute_tile(const SceneT& s, const float* tile, unsigned n, const float* T, float* acc) {
+// one warp tile (n <= kWTile points at shared address `tile`), packed projective scene
+__device__ __forceinline__ void compute_tile(const PackedScene& s, unsigned tile, unsigned n, const float* T, float* acc) {
+    const unsigned lane = threadIdx.x & 31;
+    unsigned addr = tile + 12 * lane;
+    unsigned first = lane;                         // index of this lane's first point in the group
+    const unsigned n_full = n & ~127u;
 #pragma unroll 1
-    for (unsigned i = threadIdx.x; i < n; i += kIcpThreads) {
+    for (; first < n_full; first += 128, addr += 12 * 128) group_projective<false>(s, addr, first, n, T, acc);
+    if (n_full < n) group_projective<true>(s, addr, first, n, T, acc);
+}
+
+// one warp tile, any scene with a per-point query() (nearest neighbour)
+template <class SceneT>
+__device__ __forceinline__ void compute_tile(const SceneT& s, unsigned tile, unsigned n, const float* T, float* acc) {
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (unsigned i = lane; i < n; i += 32) {
         float px, py, pz;
-        transform(T, tile[3 * i], tile[3 * i + 1], tile[3 * i + 2], px, py, pz);
+        transform(T, lds32(tile + 12 * i), lds32(tile + 12 * i + 4), lds32(tile + 12 * i + 8), px, py, pz);
         Corr c;
         if (query(s, px, py, pz, c)) accumulate(acc, px, py, pz, c);
     }
+}
+
+// the warp that deposited the last partial of a hypothesis: add the partials in chunk order (lane l
+// owns sum l), hand the 29 sums to lane 0 and run the stop logic / solve there.
+__device__ __noinline__ void warp_finish_hypothesis(HypState* st, const float* partials, unsigned n_h, pr_icp_criteria crit,
+                                                    pr_registration_result* res) {
+    const unsigned lane = threadIdx.x & 31;
+    float sum = 0.f;
+    const unsigned cb = __ldcg(&st->chunk_begin), nc = __ldcg(&st->n_chunks);
+    for (unsigned j = 0; j < nc; j++) sum += __ldcg(partials + (size_t)(cb + j) * kPartialStride + lane);
+    float S[29];
+#pragma unroll
+    for (int i = 0; i < 29; i++) S[i] = __shfl_sync(0xffffffffu, sum, i);
+    if (lane == 0) {
+        __stcg(&st->arrived, 0u);
+        finish_pass_release(st, S, n_h, crit, res);
+    }
+    __syncwarp();
+}
+
+// global -> shared copy of one tile: TMA when the source is 16-byte aligned and the copy, rounded up
+// to 16 bytes, stays inside the point buffer; otherwise the warp copies it with plain loads.
+// Returns true when the TMA path was taken (the caller then waits on the stage's mbarrier).
+__device__ __forceinline__ bool stage_tile(const float* src, unsigned n, uintptr_t pts_end, unsigned tile, unsigned bar) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned bytes = (n * 12 + 15) & ~15u;
+    const bool tma = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (reinterpret_cast<uintptr_t>(src) + bytes <= pts_end);
+    if (tma) {
+        if (lane == 0) {
+            mbar_expect_tx(bar, bytes);
+            tma_load_1d(tile, src, bytes, bar);
+        }
+    } else {
+        for (unsigned i = lane; i < n * 3; i += 32) sts32(tile + 4 * i, src[i]);
+        __syncwarp();
+    }
+    return tma;
 }
 
 template <class SceneT>
@@ -547,140 +606,112 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
                       HypState* state, float* partials, SceneT scene, pr_icp_criteria crit,
                       pr_registration_result* results) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* tile_buf[2] = {reinterpret_cast<float*>(smem_raw), reinterpret_cast<float*>(smem_raw) + kTileFloats};
-    __shared__ __align__(8) uint64_t s_full[2];
-    __shared__ float s_part[kIcpWarps][32];
-    __shared__ float s_sum[32];
-    __shared__ unsigned s_claim;
-    __shared__ int s_flag;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned tile0 = smem_u32(smem_raw) + warp * (kWStages * kWTileBytes);
+    const unsigned bar0 = smem_u32(smem_raw) + kIcpWarps * kWStages * kWTileBytes + warp * (kWStages * 8);
+    const uintptr_t pts_end = reinterpret_cast<uintptr_t>(pts) + capacity_points * 12;
+
+    if (lane == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
 
     const unsigned total = __ldcg(&ctl->total_chunks);
     const unsigned n_items = total * (unsigned)(crit.max_iteration + 1);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        mbar_init(&s_full[0], 1);
-        mbar_init(&s_full[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_claim = atomicAdd(&ctl->next_item, 1u);
+    auto claim = [&]() {
+        unsigned v = 0;
+        if (lane == 0) v = atomicAdd(&ctl->next_item, 1u);
+        return __shfl_sync(0xffffffffu, v, 0);
+    };
+    // item -> (first point pointer, number of points)
+    auto locate = [&](unsigned item, const float*& g, unsigned& n_pts) {
+        const unsigned pass = item / total;
+        const unsigned c = item - pass * total;
+        const unsigned h = __ldg(chunk_hyp + c);
+        const unsigned first = (c - __ldcg(&state[h].chunk_begin)) * kPersistChunk;
+        n_pts = min(kPersistChunk, __ldg(counts + h) - first);
+        g = pts + 3 * ((size_t)__ldg(offsets + h) + first);
+    };
+
+    unsigned stage = 0;                 // stage that holds (or will hold) the next tile to consume
+    unsigned parity = 0;                // bit s = parity to wait for on stage s
+    unsigned item = claim();
+    const float* g = pts;
+    unsigned n_pts = 0;
+    bool tma_cur = false;               // was the next tile to consume fetched by TMA?
+    if (item < n_items) {
+        locate(item, g, n_pts);
+        tma_cur = stage_tile(g, min((unsigned)kWTile, n_pts), pts_end, tile0 + stage * kWTileBytes, bar0 + 8 * stage);
     }
-    __syncthreads();
-    ItemDesc cur = describe_item(s_claim, n_items, total, pts, offsets, counts, chunk_hyp, state);
-    __syncthreads();
-    if (threadIdx.x == 0) s_claim = atomicAdd(&ctl->next_item, 1u);
-    __syncthreads();
-    ItemDesc nxt = describe_item(s_claim, n_items, total, pts, offsets, counts, chunk_hyp, state);
+    while (item < n_items) {
+        const unsigned pass = item / total;
+        const unsigned c = item - pass * total;
+        const unsigned h = __ldg(chunk_hyp + c);
+        HypState* st = state + h;
+        const unsigned n_tiles = (n_pts + kWTile - 1) / kWTile;
 
-    // a tile may be fetched by TMA when its global address is 16-byte aligned and the copy, rounded up
-    // to 16 bytes, stays inside the point buffer; otherwise all threads copy it.
-    auto tile_bytes = [&](const ItemDesc& d, unsigned t, const float*& src, unsigned& n) -> unsigned {
-        src = d.g + (size_t)t * kTileFloats;
-        n = min((unsigned)kTilePts, d.n_pts - t * kTilePts);
-        const unsigned bytes = (n * 12 + 15) & ~15u;
-        const bool ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
-                        (reinterpret_cast<uintptr_t>(src) + bytes <= reinterpret_cast<uintptr_t>(pts) + capacity_points * 12);
-        return ok ? bytes : 0u;
-    };
-    unsigned parity[2] = {0, 0};
-    bool by_tma[2] = {false, false};
-    auto issue = [&](const ItemDesc& d, unsigned t, int b) {
-        const float* src; unsigned n;
-        const unsigned bytes = tile_bytes(d, t, src, n);
-        by_tma[b] = bytes != 0;
-        if (by_tma[b] && threadIdx.x == 0) {
-            mbar_expect_tx(&s_full[b], bytes);
-            tma_load_1d(tile_buf[b], src, bytes, &s_full[b]);
-        }
-    };
-
-    int buf = 0;
-    unsigned t_cur = 0;
-    if (cur.valid) issue(cur, 0, 0);
-    float T[12];
-    float acc[32];
-    bool skip = false;
-    while (cur.valid) {
-        // ---- prefetch the tile after this one (same item, or first tile of the next claimed item)
-        const bool last_tile = (t_cur + 1 == cur.n_tiles);
-        if (!last_tile) issue(cur, t_cur + 1, buf ^ 1);
-        else if (nxt.valid) issue(nxt, 0, buf ^ 1);
-
-        // ---- first tile of an item: wait until the hypothesis has finished the previous pass
-        if (t_cur == 0) {
-            if (threadIdx.x == 0) {
-                const HypState* st = state + cur.h;
-                int flag;
-                for (;;) {
-                    if (ld_acquire(reinterpret_cast<const unsigned*>(&st->done))) { flag = 1; break; }
-                    if (ld_acquire(reinterpret_cast<const unsigned*>(&st->pass)) >= cur.pass) { flag = 0; break; }
-                    __nanosleep(100);
-                }
-                s_flag = flag;
+        // ---- wait until the hypothesis has finished the previous pass (or has returned)
+        int flag = 0;
+        if (lane == 0) {
+            unsigned backoff = 32;
+            for (;;) {
+                if (ld_relaxed(reinterpret_cast<const unsigned*>(&st->pass)) >= pass) { flag = 0; break; }
+                if (ld_relaxed(reinterpret_cast<const unsigned*>(&st->done))) { flag = 1; break; }
+                __nanosleep(backoff);
+                if (backoff < 1024) backoff <<= 1;
             }
-            __syncthreads();
-            skip = s_flag != 0;
-            if (!skip) {
-#pragma unroll
-                for (int i = 0; i < 12; i++) T[i] = __ldcg(&state[cur.h].T[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < 32; i++) acc[i] = 0.f;
         }
-
-        // ---- consume the tile
-        const float* src; unsigned n;
-        tile_bytes(cur, t_cur, src, n);
-        if (by_tma[buf]) {
-            mbar_wait(&s_full[buf], parity[buf]);
-            parity[buf] ^= 1;
-        } else if (!skip) {
-            for (unsigned i = threadIdx.x; i < n * 3; i += kIcpThreads) tile_buf[buf][i] = src[i];
-            __syncthreads();
-        }
-        if (!skip) compute_tile(scene, tile_buf[buf], n, T, acc);
-
-        // ---- last tile of the item: reduce, deposit, maybe finish the pass of this hypothesis
-        if (last_tile) {
-            if (!skip) {
-                HypState* st = state + cur.h;
-                const float mine = warp_transpose_reduce(acc);
-                s_part[warp][lane] = mine;
-                __syncthreads();
-                const unsigned c = cur.item - cur.pass * total;
-                if (warp == 0) {
-                    float s = 0.f;
+        const bool skip = __shfl_sync(0xffffffffu, flag, 0) != 0;
+        float T[12];
+        float acc[32];
 #pragma unroll
-                    for (int w = 0; w < kIcpWarps; w++) s += s_part[w][lane];
-                    __stcg(partials + (size_t)c * kPartialStride + lane, s);
-                    __threadfence();
-                    __syncwarp();
-                    int is_last = 0;
-                    if (lane == 0) is_last = (atomicAdd(&st->arrived, 1u) == __ldcg(&st->n_chunks) - 1) ? 1 : 0;
-                    is_last = __shfl_sync(0xffffffffu, is_last, 0);
-                    if (is_last) {
-                        __threadfence();
-                        float sum = 0.f;
-                        const unsigned cb = __ldcg(&st->chunk_begin), nc = __ldcg(&st->n_chunks);
-                        for (unsigned j = 0; j < nc; j++) sum += __ldcg(partials + (size_t)(cb + j) * kPartialStride + lane);
-                        s_sum[lane] = sum;
-                        __syncwarp();
-                        if (lane == 0) {
-                            st->arrived = 0;
-                            finish_pass_release(st, s_sum, cur.n_h, crit, results + cur.h);
-                        }
-                    }
+        for (int i = 0; i < 12; i++) T[i] = skip ? 0.f : __ldcg(&st->T[i]);
+#pragma unroll
+        for (int i = 0; i < 32; i++) acc[i] = 0.f;
+
+        unsigned next_item = 0xFFFFFFFFu;
+        const float* next_g = pts;
+        unsigned next_n = 0;
+        for (unsigned t = 0; t < n_tiles; t++) {
+            // ---- prefetch: next tile of this item, or the first tile of the next claimed item
+            bool tma_next = false;
+            const unsigned other = stage ^ 1;
+            if (t + 1 < n_tiles) {
+                tma_next = stage_tile(g + (size_t)(t + 1) * kWTileFloats, min((unsigned)kWTile, n_pts - (t + 1) * kWTile), pts_end,
+                                      tile0 + other * kWTileBytes, bar0 + 8 * other);
+            } else {
+                next_item = claim();
+                if (next_item < n_items) {
+                    locate(next_item, next_g, next_n);
+                    tma_next = stage_tile(next_g, min((unsigned)kWTile, next_n), pts_end, tile0 + other * kWTileBytes, bar0 + 8 * other);
                 }
             }
-            cur = nxt;
-            t_cur = 0;
-            __syncthreads();
-            if (threadIdx.x == 0) s_claim = atomicAdd(&ctl->next_item, 1u);
-            __syncthreads();
-            nxt = describe_item(s_claim, n_items, total, pts, offsets, counts, chunk_hyp, state);
-        } else {
-            t_cur++;
-            __syncthreads();   // everybody is done with tile_buf[buf] before it is refilled
+            // ---- consume tile t
+            if (tma_cur) {
+                mbar_wait(bar0 + 8 * stage, (parity >> stage) & 1u);
+                parity ^= (1u << stage);
+            }
+            if (!skip) compute_tile(scene, tile0 + stage * kWTileBytes, min((unsigned)kWTile, n_pts - t * kWTile), T, acc);
+            __syncwarp();            // every lane is done with this stage before it is refilled
+            stage = other;
+            tma_cur = tma_next;
         }
-        buf ^= 1;
+
+        // ---- item complete: reduce over the warp, deposit, maybe finish the pass of this hypothesis
+        if (!skip) {
+            const float mine = warp_transpose_reduce(acc);     // lane l = sum of value l
+            __stcg(partials + (size_t)c * kPartialStride + lane, mine);
+            __syncwarp();            // all 32 partial stores precede lane 0's release below
+            int is_last = 0;
+            if (lane == 0) is_last = (atom_add_release(&st->arrived, 1u) == __ldcg(&st->n_chunks) - 1) ? 1 : 0;
+            is_last = __shfl_sync(0xffffffffu, is_last, 0);
+            if (is_last) warp_finish_hypothesis(st, partials, __ldg(counts + h), crit, results + h);
+        }
+        item = next_item;
+        g = next_g;
+        n_pts = next_n;
     }
 }
 
@@ -751,7 +782,7 @@ template <class SceneT>
 int persistent_grid(int* grid_out) {
     static int cached = 0;
     if (!cached) {
-        const int smem = 2 * kTileFloats * 4;
+        const int smem = kPersistSmem;
         PR_CUDA_TRY(cudaFuncSetAttribute(icp_persistent_kernel<SceneT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ = 0, dev = 0, sms = 0;
         PR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_persistent_kernel<SceneT>, kIcpThreads, smem));
@@ -793,7 +824,7 @@ int run_icp(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_
     grid = (int)std::min<size_t>((size_t)grid, max_items);
     icp_plan_kernel<<<1, kIcpThreads, 0, stream>>>(counts_dev, (uint32_t)n_hyp, kPersistChunk, ws.state, ws.chunk_hyp,
                                                    (uint32_t)ws.max_chunks, &ws.ctl->total_chunks, results_dev, &ws.ctl->next_item);
-    icp_persistent_kernel<PScene><<<grid, kIcpThreads, 2 * kTileFloats * 4, stream>>>(
+    icp_persistent_kernel<PScene><<<grid, kIcpThreads, kPersistSmem, stream>>>(
         pts_dev, capacity_points, offsets_dev, counts_dev, ws.chunk_hyp, ws.ctl, ws.state, ws.partials, pscene, crit, results_dev);
     count_launch(2);
     if (flags & PR_ICP_UPDATE_POINTS) {
@@ -884,7 +915,7 @@ int pr_icp_projective_batch(float* pts_dev, const uint32_t* offsets_dev, const u
     cudaStream_t stream = as_stream(stream_);
     PackedScene ps;
     ps.W = s.W; ps.H = s.H; ps.fW = s.fW; ps.fH = s.fH; ps.max_dist = s.max_dist;
-    ps.fx = s.fx; ps.fy = s.fy; ps.cx = s.cx; ps.cy = s.cy; ps.qn = ws.packed; ps.n2 = ws.packed2;
+    ps.fx = s.fx; ps.fy = s.fy; ps.cx05 = s.cx + 0.5f; ps.cy05 = s.cy + 0.5f; ps.qn = ws.packed; ps.n2 = ws.packed2;
     if (!use_pass_driver()) {
         scene_pack_kernel<<<(unsigned)((n_px + 255) / 256), 256, 0, stream>>>(s.pcd, s.nrm, n_px, ws.packed, ws.packed2);
         count_launch();

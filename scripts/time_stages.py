@@ -28,12 +28,15 @@ L = _lib.lib()
 
 def timed(fn):
     fn(); torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(reps): fn()
-    b.record(); torch.cuda.synchronize()
-    return a.elapsed_time(b) / reps
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    out.setdefault("raw", {})[len(out["raw"])] = [round(t, 3) for t in ts]
+    return float(np.median(ts))
 
+out = {}
 out = {"impl": os.environ.get("PR_ICP_IMPL", "persistent"), "hyp": P, "model_points": n_pts}
 out["step_ms"] = timed(lambda: ref.run_device(poses, crit))
 out["icp_ms"] = timed(lambda: api.icp_batch(pts, offsets, counts, scene, crit))
