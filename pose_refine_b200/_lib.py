@@ -64,11 +64,12 @@ def lib():
     """The loaded library; raises (never falls back) when it has not been built."""
     global _dll
     if _dll is None:
-        if not os.path.exists(LIB):
+        path = os.environ.get("PR_LIB", LIB)   # experiments: alternative builds of the same library
+        if not os.path.exists(path):
             raise ImportError(
                 f"{LIB} is missing: build it with `python -m pose_refine_b200.build` "
                 "(nvcc, sm_100a). pose_refine_b200 has no CPU fallback.")
-        dll = C.CDLL(LIB)
+        dll = C.CDLL(path)
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(dll, name)  # AttributeError if the header and the library disagree
             fn.restype, fn.argtypes = res, args

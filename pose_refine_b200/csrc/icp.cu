@@ -39,6 +39,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 namespace prb {
 
@@ -406,12 +407,33 @@ icp_pass_kernel(const float* __restrict__ pts, const uint32_t* __restrict__ offs
 // reduce its 29 sums with the transposing butterfly and deposit one partial per item.  There is no
 // CTA-wide barrier anywhere; the only cross-warp synchronisation is the per-hypothesis
 // acquire/release on HypState::pass / done and the ticket counter.
-constexpr int kWTile = 512;                    // points per warp tile (6 KB)
+#ifndef PR_WTILE
+#define PR_WTILE 512
+#endif
+#ifndef PR_CHUNK
+#define PR_CHUNK 2048
+#endif
+// Tuning (measured on B200, 512 hypotheses x 31 passes, ICP only): ILP 4 / 2 CTAs per SM 2.83 ms;
+// ILP 8 / 1 CTA of 256 threads 2.29 ms; ILP 8 / 384 threads 2.68 ms; tile 256 2.62 ms.  Eight gathers in
+// flight per lane with few, register-rich warps beats more warps with fewer gathers each.
+#ifndef PR_ILP
+#define PR_ILP 8
+#endif
+#ifndef PR_MINB
+#define PR_MINB 1
+#endif
+#ifndef PR_PTHREADS
+#define PR_PTHREADS 256
+#endif
+constexpr int kPThreads = PR_PTHREADS;         // threads per CTA of the persistent kernel
+constexpr int kPWarps = kPThreads / 32;
+constexpr int kWTile = PR_WTILE;               // points per warp tile (6 KB at 512)
 constexpr int kWTileFloats = kWTile * 3;
 constexpr int kWTileBytes = kWTileFloats * 4;
 constexpr int kWStages = 2;
-constexpr uint32_t kPersistChunk = 2048;       // points per work item (4 tiles, 64 points per lane)
-constexpr int kPersistSmem = kIcpWarps * kWStages * kWTileBytes + kIcpWarps * kWStages * 8;
+constexpr uint32_t kPersistChunk = PR_CHUNK;   // points per work item
+constexpr int kIlp = PR_ILP;                   // points per lane per group (gathers in flight per lane)
+constexpr int kPersistSmem = kPWarps * kWStages * kWTileBytes + kPWarps * kWStages * 8;
 
 struct IcpCtl {            // device-side control block
     unsigned next_item;    // work-item claim counter
@@ -492,8 +514,8 @@ __device__ __forceinline__ float fast_rcp(float z) {
     return fmaf(r, e, r);
 }
 
-// 128 consecutive points of a tile against the packed projective scene: lane l owns points
-// l, 32+l, 64+l, 96+l, so each of the four gather instructions covers 32 CONSECUTIVE model points --
+// 32*kIlp consecutive points of a tile against the packed projective scene: lane l owns points
+// l, 32+l, 64+l, ..., so each of the four gather instructions covers 32 CONSECUTIVE model points --
 // neighbouring scene pixels, i.e. 4 cache lines per 128-bit gather instead of 16.  The four gathers
 // are issued before any of them is consumed.
 // Pixel selection: u = int(px/pz*fx + cx + 0.5) (common.h:63-73) evaluated as
@@ -503,11 +525,11 @@ __device__ __forceinline__ float fast_rcp(float z) {
 template <bool TAIL>
 __device__ __forceinline__ void group_projective(const PackedScene& s, unsigned addr, unsigned first, unsigned n,
                                                  const float* T, float* acc) {
-    float px[4], py[4], pz[4];
-    int idx[4];
-    bool ok[4];
+    float px[kIlp], py[kIlp], pz[kIlp];
+    int idx[kIlp];
+    bool ok[kIlp];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < kIlp; k++) {
         const float x = lds32(addr + 384 * k), y = lds32(addr + 384 * k + 4), z = lds32(addr + 384 * k + 8);
         transform(T, x, y, z, px[k], py[k], pz[k]);
         const float rz = fast_rcp(pz[k]);
@@ -517,17 +539,17 @@ __device__ __forceinline__ void group_projective(const PackedScene& s, unsigned 
         if (TAIL) ok[k] = ok[k] & (first + 32 * k < n);
         idx[k] = vi * s.W + ui;
     }
-    float4 A[4];
-    float2 B[4];
+    float4 A[kIlp];
+    float2 B[kIlp];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < kIlp; k++) {
         if (ok[k]) {
             A[k] = __ldg(s.qn + idx[k]);
             B[k] = __ldg(s.n2 + idx[k]);
         }
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < kIlp; k++) {
         if (ok[k]) {
             if (A[k].z > 0.f && fabsf(pz[k] - A[k].z) <= s.max_dist) {       // depth_scene.h:42
                 Corr cr;
@@ -543,9 +565,10 @@ __device__ __forceinline__ void compute_tile(const PackedScene& s, unsigned tile
     const unsigned lane = threadIdx.x & 31;
     unsigned addr = tile + 12 * lane;
     unsigned first = lane;                         // index of this lane's first point in the group
-    const unsigned n_full = n & ~127u;
+    constexpr unsigned kGroup = 32 * kIlp;
+    const unsigned n_full = n - n % kGroup;
 #pragma unroll 1
-    for (; first < n_full; first += 128, addr += 12 * 128) group_projective<false>(s, addr, first, n, T, acc);
+    for (; first < n_full; first += kGroup, addr += 12 * kGroup) group_projective<false>(s, addr, first, n, T, acc);
     if (n_full < n) group_projective<true>(s, addr, first, n, T, acc);
 }
 
@@ -600,7 +623,7 @@ __device__ __forceinline__ bool stage_tile(const float* src, unsigned n, uintptr
 }
 
 template <class SceneT>
-__global__ void __launch_bounds__(kIcpThreads, 2)
+__global__ void __launch_bounds__(kPThreads, PR_MINB)
 icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, const uint32_t* __restrict__ offsets,
                       const uint32_t* __restrict__ counts, const uint32_t* __restrict__ chunk_hyp, IcpCtl* ctl,
                       HypState* state, float* partials, SceneT scene, pr_icp_criteria crit,
@@ -608,7 +631,7 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned tile0 = smem_u32(smem_raw) + warp * (kWStages * kWTileBytes);
-    const unsigned bar0 = smem_u32(smem_raw) + kIcpWarps * kWStages * kWTileBytes + warp * (kWStages * 8);
+    const unsigned bar0 = smem_u32(smem_raw) + kPWarps * kWStages * kWTileBytes + warp * (kWStages * 8);
     const uintptr_t pts_end = reinterpret_cast<uintptr_t>(pts) + capacity_points * 12;
 
     if (lane == 0) {
@@ -772,6 +795,7 @@ inline IcpWs carve_icp_ws(void* base, size_t n_hyp, size_t capacity_points, size
     return ws;
 }
 
+// PR_ICP_IMPL=pass selects the first-generation driver (one launch per pass) for cross-checks
 inline bool use_pass_driver() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("PR_ICP_IMPL"); v = (e && strcmp(e, "pass") == 0) ? 1 : 0; }
@@ -785,7 +809,7 @@ int persistent_grid(int* grid_out) {
         const int smem = kPersistSmem;
         PR_CUDA_TRY(cudaFuncSetAttribute(icp_persistent_kernel<SceneT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ = 0, dev = 0, sms = 0;
-        PR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_persistent_kernel<SceneT>, kIcpThreads, smem));
+        PR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_persistent_kernel<SceneT>, kPThreads, smem));
         PR_CUDA_TRY(cudaGetDevice(&dev));
         PR_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         cached = std::max(1, occ) * std::max(1, sms);
@@ -816,15 +840,15 @@ int run_icp(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_
         PR_LAUNCH_CHECK();
         return PR_OK;
     }
+    const size_t max_items = (capacity_points / kPersistChunk + n_hyp + 1) * (size_t)(crit.max_iteration + 1);
+    if (max_items > 0x7FFFFFFFull) return PR_ERR_INVALID_ARGUMENT;
+    icp_plan_kernel<<<1, kIcpThreads, 0, stream>>>(counts_dev, (uint32_t)n_hyp, kPersistChunk, ws.state, ws.chunk_hyp,
+                                                   (uint32_t)ws.max_chunks, &ws.ctl->total_chunks, results_dev, &ws.ctl->next_item);
     int grid = 0;
     int rc = persistent_grid<PScene>(&grid);
     if (rc != PR_OK) return rc;
-    const size_t max_items = (capacity_points / kPersistChunk + n_hyp + 1) * (size_t)(crit.max_iteration + 1);
-    if (max_items > 0x7FFFFFFFull) return PR_ERR_INVALID_ARGUMENT;
-    grid = (int)std::min<size_t>((size_t)grid, max_items);
-    icp_plan_kernel<<<1, kIcpThreads, 0, stream>>>(counts_dev, (uint32_t)n_hyp, kPersistChunk, ws.state, ws.chunk_hyp,
-                                                   (uint32_t)ws.max_chunks, &ws.ctl->total_chunks, results_dev, &ws.ctl->next_item);
-    icp_persistent_kernel<PScene><<<grid, kIcpThreads, kPersistSmem, stream>>>(
+    grid = (int)std::min<size_t>((size_t)grid, (max_items + kPWarps - 1) / kPWarps);
+    icp_persistent_kernel<PScene><<<grid, kPThreads, kPersistSmem, stream>>>(
         pts_dev, capacity_points, offsets_dev, counts_dev, ws.chunk_hyp, ws.ctl, ws.state, ws.partials, pscene, crit, results_dev);
     count_launch(2);
     if (flags & PR_ICP_UPDATE_POINTS) {

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+: > gpurun_out/variants.jsonl
+for f in pose_refine_b200/variants/lib_*.so; do
+  PR_LIB=$PWD/$f timeout 200 python scripts/time_icp.py 512 8 >> gpurun_out/variants.jsonl 2>> gpurun_out/variants.err
+done
+cat gpurun_out/variants.jsonl; tail -3 gpurun_out/variants.err

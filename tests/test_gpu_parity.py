@@ -369,10 +369,26 @@ def test_full_size_properties(api, port, mesh, fixture_scene, golden, torch_mod)
     R = r[:, :16].reshape(P, 4, 4)[:, :3, :3].astype(np.float64)
     assert np.abs(R @ R.transpose(0, 2, 1) - np.eye(3)).max() < 1e-4, "accumulated updates stay rotations"
     assert np.isfinite(r).all() and (r[:, 17] >= 0).all() and (r[:, 17] <= 1).all() and (r[:, 17] > 0.5).mean() > 0.7
-    # spot-check hypotheses against the oracle end to end
+    # spot-check hypotheses against the oracle end to end.  ICP on a poor hypothesis is chaotic: the
+    # reference's own CPU code run with a different thread count (= another float summation order)
+    # moves the final pose of a NON-converging hypothesis by O(1) and of a converging one by up to
+    # ~6e-5 (measured on this batch).  So each sampled hypothesis is held to
+    #     max(1e-4, 3 x the oracle's own spread over thread counts 1/2/5/8),
+    # and at least 70% of the sample must be reproducible (spread <= 3e-5) so the check is not vacuous.
     ps = port.scene_projective(fixture_scene["scene_depth"], K)
-    for i in (0, 137, 511):
+    sample = list(range(0, P, 32))
+    reproducible = 0
+    for i in sample:
         d = port.render(mesh, poses[i: i + 1], 640, 480, arrays["proj"])[0]
         assert np.array_equal(a[i].cpu().numpy(), d)
-        want = port.icp(ps, port.depth2cloud(d, K), 0.0, 0.0, 30)["raw"]
-        assert_result_close(r[i], want, f"hyp {i} of 512")
+        cloud = port.depth2cloud(d, K)
+        runs = []
+        for nt in (1, 2, 5, 8):
+            port.set_threads(nt)
+            runs.append(port.icp(ps, cloud, 0.0, 0.0, 30)["raw"][:16].astype(np.float64))
+        port.set_threads(1)
+        spread = max(np.abs(runs[0] - x).max() for x in runs[1:])
+        reproducible += spread <= 3e-5
+        err = np.abs(r[i, :16] - runs[0]).max()
+        assert err <= max(REL_TOL, 3 * spread), f"hyp {i}: |T_gpu - T_oracle| = {err:.2e}, oracle's own spread {spread:.2e}"
+    assert reproducible >= 0.7 * len(sample), f"only {reproducible}/{len(sample)} sampled hypotheses are reproducible"
