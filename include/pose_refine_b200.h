@@ -90,6 +90,15 @@ const char* pr_error_string(int status);
 /* PR_OK iff the current CUDA device can run this library (compute capability 10.x). */
 int pr_device_check(void);
 
+/* Device memory helpers so that C / C++ hosts above this ABI need no CUDA headers: they replace  */
+/* the cudaMalloc / cudaFree / thrust::copy calls inside device_vector_holder<T>                   */
+/* (cuda_icp/scene/common.cu:3-40, cuda_renderer/renderer.cu:15-50).                              */
+int pr_device_malloc(void** ptr, size_t bytes);
+int pr_device_free(void* ptr);
+int pr_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes, pr_stream_t stream);   /* synchronises */
+int pr_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes, pr_stream_t stream);   /* synchronises */
+int pr_stream_synchronize(pr_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------- */
 /* mesh ingestion: replaces cuda_renderer::Model::LoadModel (renderer.cpp:16-58, assimp).       */
 /* Reads an ASCII or binary_little_endian PLY; writes triangles in face order as 9 floats each  */

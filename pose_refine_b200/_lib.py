@@ -31,6 +31,11 @@ PROTOTYPES = {
     "pr_version": (_i, []),
     "pr_error_string": (C.c_char_p, [_i]),
     "pr_device_check": (_i, []),
+    "pr_device_malloc": (_i, [C.POINTER(_vp), _sz]),
+    "pr_device_free": (_i, [_vp]),
+    "pr_memcpy_h2d": (_i, [_vp, _vp, _sz, _vp]),
+    "pr_memcpy_d2h": (_i, [_vp, _vp, _sz, _vp]),
+    "pr_stream_synchronize": (_i, [_vp]),
     "pr_load_ply": (_i, [C.c_char_p, _vp, _sz, C.POINTER(_sz)]),
     "pr_compute_proj": (_i, [_vp, _i, _i, _f, _f, _vp]),
     "pr_render_workspace_bytes": (_sz, [_sz, _sz, _sz, _sz]),

@@ -93,6 +93,32 @@ int pr_device_check(void) {
     return (p.major == 10) ? PR_OK : PR_ERR_NO_DEVICE;
 }
 
+int pr_device_malloc(void** ptr, size_t bytes) {
+    if (!ptr) return PR_ERR_INVALID_ARGUMENT;
+    PR_CUDA_TRY(cudaMalloc(ptr, bytes ? bytes : 1));
+    return PR_OK;
+}
+int pr_device_free(void* ptr) {
+    PR_CUDA_TRY(cudaFree(ptr));
+    return PR_OK;
+}
+int pr_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes, pr_stream_t stream) {
+    if (bytes == 0) return PR_OK;
+    PR_CUDA_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, prb::as_stream(stream)));
+    PR_CUDA_TRY(cudaStreamSynchronize(prb::as_stream(stream)));
+    return PR_OK;
+}
+int pr_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes, pr_stream_t stream) {
+    if (bytes == 0) return PR_OK;
+    PR_CUDA_TRY(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, prb::as_stream(stream)));
+    PR_CUDA_TRY(cudaStreamSynchronize(prb::as_stream(stream)));
+    return PR_OK;
+}
+int pr_stream_synchronize(pr_stream_t stream) {
+    PR_CUDA_TRY(cudaStreamSynchronize(prb::as_stream(stream)));
+    return PR_OK;
+}
+
 int pr_refiner_create(pr_refiner** out, const float* tris_host, size_t n_tris, uint32_t width, uint32_t height,
                       const float K[9], size_t max_hyp, size_t capacity_points) {
     if (!out || !tris_host || !K || n_tris == 0 || width == 0 || height == 0 || max_hyp == 0) return PR_ERR_INVALID_ARGUMENT;
