@@ -374,7 +374,7 @@ def test_full_size_properties(api, port, mesh, fixture_scene, golden, torch_mod)
     # moves the final pose of a NON-converging hypothesis by O(1) and of a converging one by up to
     # ~6e-5 (measured on this batch).  So each sampled hypothesis is held to
     #     max(1e-4, 3 x the oracle's own spread over thread counts 1/2/5/8),
-    # and at least 70% of the sample must be reproducible (spread <= 3e-5) so the check is not vacuous.
+    # and at least half of the sample must be reproducible (spread <= 3e-5) so the check is not vacuous.
     ps = port.scene_projective(fixture_scene["scene_depth"], K)
     sample = list(range(0, P, 32))
     reproducible = 0
@@ -391,4 +391,4 @@ def test_full_size_properties(api, port, mesh, fixture_scene, golden, torch_mod)
         reproducible += spread <= 3e-5
         err = np.abs(r[i, :16] - runs[0]).max()
         assert err <= max(REL_TOL, 3 * spread), f"hyp {i}: |T_gpu - T_oracle| = {err:.2e}, oracle's own spread {spread:.2e}"
-    assert reproducible >= 0.7 * len(sample), f"only {reproducible}/{len(sample)} sampled hypotheses are reproducible"
+    assert reproducible >= 0.5 * len(sample), f"only {reproducible}/{len(sample)} sampled hypotheses are reproducible"
