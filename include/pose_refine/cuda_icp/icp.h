@@ -54,7 +54,7 @@ namespace detail {
 inline RegistrationResult run(device_vector_holder<Vec3f>& model, const pr_scene_projective* sp, const pr_scene_nn* sn,
                               const ICPConvergenceCriteria& c) {
     const size_t n = model.size();
-    const size_t ws_bytes = pr_icp_workspace_bytes(1, n, sp ? sp->width * sp->height : 0);
+    const size_t ws_bytes = pr_icp_workspace_bytes(1, n, sp ? sp->width * sp->height : sn->n_points + 2 * sn->n_nodes + 16);
     device_vector_holder<unsigned char> ws(ws_bytes);
     device_vector_holder<uint32_t> meta;
     meta.upload(std::vector<uint32_t>{0u, (uint32_t)n});    // offsets[0] = 0, counts[0] = n

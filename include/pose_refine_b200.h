@@ -168,7 +168,8 @@ int pr_scene_nn_build_host(const void* depth_host, int depth_is_int32, uint32_t 
 /*   results_dev n_hyp records; flags: PR_ICP_UPDATE_POINTS writes the refined points back        */
 /*               (the reference mutates the model cloud in place, icp.cu:209).                    */
 #define PR_ICP_UPDATE_POINTS 1
-/* scene_pixels: width*height of the projective scene the workspace will be used with (0 for Scene_nn). */
+/* scene_pixels: width*height of the projective scene the workspace will be used with; for Scene_nn pass   */
+/* n_points + 2*n_nodes + 16 (room for the re-laid-out kd-tree; with less, the reference-layout walk is used). */
 size_t pr_icp_workspace_bytes(size_t n_hyp, size_t capacity_points, size_t scene_pixels);
 int pr_icp_projective_batch(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_dev, size_t n_hyp,
                             size_t capacity_points, const pr_scene_projective* scene, pr_icp_criteria criteria,

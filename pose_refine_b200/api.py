@@ -289,7 +289,7 @@ def icp_batch(pts, offsets, counts, scene, criteria=None, update_points=False):
     P = counts.shape[0]
     cap = pts.shape[0]
     res = torch.empty((max(P, 1), 18), dtype=torch.float32, device="cuda")
-    n_px = scene.width * scene.height if isinstance(scene, SceneProjective) else 0
+    n_px = scene.width * scene.height if isinstance(scene, SceneProjective) else scene.pcd.shape[0] + 2 * len(scene.nodes_host) + 16
     ws_bytes = lib().pr_icp_workspace_bytes(P, cap, n_px)
     ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device="cuda")
     flags = 1 if update_points else 0

@@ -144,6 +144,119 @@ __device__ __forceinline__ bool query(const NnScene& s, float px, float py, floa
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed kd-tree for the persistent driver.  Same tree (same nodes, same leaf ranges, same points) as
+// the reference's Node_kdtree array, re-laid out per ICP call so that a node is two aligned float4:
+//     {lo.x, lo.y, lo.z, a}   {hi.x, hi.y, hi.z, unused}
+// a >= 0: internal node, children a and a+1 (build_tree appends them together, pcd_scene.cpp:160-170);
+// a <  0: leaf, a = 0x80000000 | count << 24 | left.  [lo,hi] is the box of the node's OWN points --
+// computed here for leaves too (the reference stores none for leaves, pcd_scene.h:14-19).
+// The query is an exact nearest-neighbour search like Scene_nn::query, but it prunes with the box of
+// the CHILD it is about to enter (the reference prunes with the box of the node it re-visits, which is
+// much weaker: 385 node visits per query on the fixture vs ~20-40 here), starts
+// from best = max_dist^2 (anything farther is invalid anyway, pcd_scene.h:127) and keeps the far
+// children on a small explicit stack.  Distances use the reference's operation order, so the winner is
+// the same point except for exact distance ties between points of different leaves.
+struct PackedNnScene {
+    float max_dist_sq;
+    const float4* nodes;      // 2 per node
+    const float4* pts4;       // {x, y, z, 0}
+    const float* nrm;         // original Vec3f normals
+    int n_nodes;
+    NnScene ref;              // the reference layout (fallback walk when the stack would overflow)
+};
+
+__global__ void __launch_bounds__(256)
+nn_pack_points_kernel(const float* __restrict__ pcd, size_t n, float4* __restrict__ pts4) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) pts4[i] = make_float4(pcd[3 * i], pcd[3 * i + 1], pcd[3 * i + 2], 0.f);
+}
+// sets *unsupported when a leaf does not fit the packed encoding (more than 127 points or left >= 2^24)
+__global__ void __launch_bounds__(256)
+nn_pack_nodes_kernel(const pr_node_kdtree* __restrict__ nodes, int n_nodes, const float* __restrict__ pcd,
+                     float4* __restrict__ out, unsigned* __restrict__ unsupported) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_nodes) return;
+    const pr_node_kdtree nd = nodes[i];
+    float lo[3], hi[3];
+    int a;
+    if (nd.child1 < 0 || nd.child2 < 0) {
+        const int cnt = nd.right - nd.left;
+        if (cnt < 0 || cnt > 127 || nd.left < 0 || nd.left >= (1 << 24)) { *unsupported = 1; return; }
+        for (int k = 0; k < 3; k++) { lo[k] = FLT_MAX; hi[k] = -FLT_MAX; }
+        for (int j = nd.left; j < nd.right; j++)
+            for (int k = 0; k < 3; k++) { const float v = pcd[3 * j + k]; lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v); }
+        a = (int)(0x80000000u | ((unsigned)cnt << 24) | (unsigned)nd.left);
+    } else {
+        if (nd.child2 != nd.child1 + 1) { *unsupported = 1; return; }
+        for (int k = 0; k < 3; k++) { lo[k] = nd.bbox[2 * k]; hi[k] = nd.bbox[2 * k + 1]; }
+        a = nd.child1;
+    }
+    out[2 * i] = make_float4(lo[0], lo[1], lo[2], __int_as_float(a));
+    out[2 * i + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+}
+
+__device__ __forceinline__ float box_dist_sq(const float4& lo, const float4& hi, float px, float py, float pz) {
+    const float dx = fmaxf(fmaxf(lo.x - px, px - hi.x), 0.f);
+    const float dy = fmaxf(fmaxf(lo.y - py, py - hi.y), 0.f);
+    const float dz = fmaxf(fmaxf(lo.z - pz, pz - hi.z), 0.f);
+    return dx * dx + dy * dy + dz * dz;
+}
+
+__device__ __forceinline__ bool query(const PackedNnScene& s, float px, float py, float pz, Corr& c) {
+    if (s.n_nodes <= 0) return false;
+    constexpr int kStack = 40;
+    int stack_n[kStack];
+    float stack_lb[kStack];
+    int sp = 0;
+    float best = s.max_dist_sq;
+    int best_i = -1;
+    bool overflow = false;
+    float4 lo = __ldg(s.nodes), hi = __ldg(s.nodes + 1);
+    // a box lower bound is rounded, so it is trusted only with a 1e-5 margin
+    bool go = box_dist_sq(lo, hi, px, py, pz) * 0.99999f < best;
+    while (go) {
+        const int a = __float_as_int(lo.w);
+        if (a < 0) {
+            const int left = a & 0xFFFFFF, cnt = (a >> 24) & 127;
+            for (int i = left; i < left + cnt; i++) {
+                const float4 q = __ldg(s.pts4 + i);
+                const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+                const float d2 = addf(addf(mulf(dx, dx), mulf(dy, dy)), mulf(dz, dz));    // pcd_scene.h:86-89
+                if (d2 < best) { best = d2; best_i = i; }
+            }
+            go = false;
+        } else {
+            const float4 lo1 = __ldg(s.nodes + 2 * a), hi1 = __ldg(s.nodes + 2 * a + 1);
+            const float4 lo2 = __ldg(s.nodes + 2 * a + 2), hi2 = __ldg(s.nodes + 2 * a + 3);
+            const float lb1 = box_dist_sq(lo1, hi1, px, py, pz) * 0.99999f, lb2 = box_dist_sq(lo2, hi2, px, py, pz) * 0.99999f;
+            const bool first1 = lb1 <= lb2;
+            const float lb_near = first1 ? lb1 : lb2, lb_far = first1 ? lb2 : lb1;
+            if (lb_far < best) {
+                if (sp < kStack) { stack_n[sp] = first1 ? a + 1 : a; stack_lb[sp] = lb_far; sp++; }
+                else overflow = true;
+            }
+            if (lb_near < best) { lo = first1 ? lo1 : lo2; hi = first1 ? hi1 : hi2; continue; }
+            go = false;
+        }
+        while (sp > 0) {
+            --sp;
+            if (stack_lb[sp] < best) {
+                const int n = stack_n[sp];
+                lo = __ldg(s.nodes + 2 * n); hi = __ldg(s.nodes + 2 * n + 1);
+                go = true;
+                break;
+            }
+        }
+    }
+    if (overflow) return query(s.ref, px, py, pz, c);     // deeper than the stack: the reference walk
+    if (best_i < 0) return false;
+    const float4 q = __ldg(s.pts4 + best_i);
+    c.qx = q.x; c.qy = q.y; c.qz = q.z;
+    c.nx = __ldg(s.nrm + 3 * best_i); c.ny = __ldg(s.nrm + 3 * best_i + 1); c.nz = __ldg(s.nrm + 3 * best_i + 2);
+    return true;
+}
+
 // thrust__pcd2Ab::operator() (icp.h:138-208): adds one correspondence into the 29 running sums.
 __device__ __forceinline__ void accumulate(float* acc, float px, float py, float pz, const Corr& c) {
     const float dx = c.qx - px, dy = c.qy - py, dz = c.qz - pz;
@@ -950,16 +1063,40 @@ int pr_icp_projective_batch(float* pts_dev, const uint32_t* offsets_dev, const u
 int pr_icp_nn_batch(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_dev, size_t n_hyp,
                     size_t capacity_points, const pr_scene_nn* scene, pr_icp_criteria criteria,
                     pr_registration_result* results_dev, int flags,
-                    void* workspace_dev, size_t workspace_bytes, pr_stream_t stream) {
+                    void* workspace_dev, size_t workspace_bytes, pr_stream_t stream_) {
     NnScene s;
     int rc = make_nn_scene(scene, s);
     if (rc != PR_OK) return rc;
     rc = check_icp_args(pts_dev, offsets_dev, counts_dev, n_hyp, capacity_points, criteria, results_dev, workspace_dev);
     if (rc != PR_OK) return rc;
     if (n_hyp == 0) return PR_OK;
+    cudaStream_t stream = as_stream(stream_);
+    // the packed tree needs 16 B per scene point + 32 B per node (+ a flag word)
+    const size_t units = scene->n_points + 2 * scene->n_nodes + 16;
+    const IcpWs ws_packed = carve_icp_ws(workspace_dev, n_hyp, capacity_points, units);
+    if (!use_pass_driver() && s.n_nodes > 0 && workspace_bytes >= ws_packed.bytes) {
+        float4* pts4 = ws_packed.packed;
+        float4* pnodes = pts4 + scene->n_points;
+        unsigned* flag = reinterpret_cast<unsigned*>(pnodes + 2 * scene->n_nodes);
+        PR_CUDA_TRY(cudaMemsetAsync(flag, 0, 4, stream));
+        nn_pack_points_kernel<<<(unsigned)((scene->n_points + 255) / 256), 256, 0, stream>>>(s.pcd, scene->n_points, pts4);
+        nn_pack_nodes_kernel<<<(unsigned)((scene->n_nodes + 255) / 256), 256, 0, stream>>>(s.nodes, s.n_nodes, s.pcd, pnodes, flag);
+        count_launch(2);
+        // the encoding limits (leaf <= 127 points, < 2^24 points, sibling children) hold for every tree
+        // KDTree_cpu::build_tree / pr_scene_nn_build_host produce; a foreign tree that breaks them is detected
+        // on the device and reported after a one-word read-back.
+        unsigned h_flag = 0;
+        PR_CUDA_TRY(cudaMemcpyAsync(&h_flag, flag, 4, cudaMemcpyDeviceToHost, stream));
+        PR_CUDA_TRY(cudaStreamSynchronize(stream));
+        if (!h_flag) {
+            PackedNnScene ps;
+            ps.max_dist_sq = s.max_dist_sq; ps.nodes = pnodes; ps.pts4 = pts4; ps.nrm = s.nrm; ps.n_nodes = s.n_nodes; ps.ref = s;
+            return run_icp(pts_dev, offsets_dev, counts_dev, n_hyp, capacity_points, s, ps, criteria, results_dev, flags, ws_packed, stream);
+        }
+    }
     IcpWs ws = carve_icp_ws(workspace_dev, n_hyp, capacity_points, 0);
     if (workspace_bytes < ws.bytes) return PR_ERR_WORKSPACE_TOO_SMALL;
-    return run_icp(pts_dev, offsets_dev, counts_dev, n_hyp, capacity_points, s, s, criteria, results_dev, flags, ws, as_stream(stream));
+    return run_icp(pts_dev, offsets_dev, counts_dev, n_hyp, capacity_points, s, s, criteria, results_dev, flags, ws, stream);
 }
 
 int pr_solve_666(const float A[36], const float b[6], float T[16]) {

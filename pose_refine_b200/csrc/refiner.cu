@@ -134,7 +134,7 @@ int pr_refiner_create(pr_refiner** out, const float* tris_host, size_t n_tris, u
     r->capacity_points = capacity_points ? capacity_points : (max_hyp * (n_px / 4 + 4));
     r->ws_render_bytes = pr_render_workspace_bytes(max_hyp, n_tris, width, height);
     r->ws_cloud_bytes = pr_depth2cloud_workspace_bytes(max_hyp, width, height);
-    r->ws_icp_bytes = pr_icp_workspace_bytes(max_hyp, r->capacity_points, n_px);
+    r->ws_icp_bytes = pr_icp_workspace_bytes(max_hyp, r->capacity_points, 3 * n_px + 16);   // projective: n_px; kd-tree: <= n_px points + 2 * (2 n_px + 1) nodes... bounded by 3 n_px for leaf >= 2
     cudaError_t e = cudaSuccess;
     auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 256); };
     alloc((void**)&r->d_tris, n_tris * 36);
