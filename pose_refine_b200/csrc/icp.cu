@@ -277,6 +277,98 @@ __device__ __forceinline__ void accumulate(float* acc, float px, float py, float
     acc[28] += 1.0f;
 }
 
+// ---- packed accumulation (sm_100 FFMA2) ------------------------------------------------------------
+// Blackwell has a two-wide FP32 FMA (PTX fma.rn.f32x2, SASS FFMA2) whose first multiplicand may be a
+// scalar broadcast.  The 21 + 6 products J_i*J_j, J_i*r are rows "J_i x (J_i..J_5, r)", so with J and r
+// parked in the pairs E0=(J0,J1) E1=(J2,J3) E2=(J4,J5) E3=(r,0) they take 18 FFMA2 instead of 27 FFMA
+// (row 1, 3, 5 start on an odd element: that lane recomputes the symmetric product and is ignored).
+struct Acc2 {
+    float2 p[18];      // see unpack_acc2 for the slot -> Vec29f index map
+    float2 dd;         // sum dx^2, sum dy^2
+    float dz2, cnt;
+};
+__device__ __forceinline__ float2 ffma2(float a, float2 b, float2 c) {     // a * b + c, a broadcast
+    float2 d;
+    asm("{\n"
+        ".reg .b64 ra, rb, rc, rd;\n"
+        "mov.b64 ra, {%2, %2};\n"
+        "mov.b64 rb, {%3, %4};\n"
+        "mov.b64 rc, {%5, %6};\n"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n"
+        "mov.b64 {%0, %1}, rd;\n"
+        "}\n" : "=f"(d.x), "=f"(d.y) : "f"(a), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 ffma2v(float2 a, float2 b, float2 c) {   // element-wise a * b + c
+    float2 d;
+    asm("{\n"
+        ".reg .b64 ra, rb, rc, rd;\n"
+        "mov.b64 ra, {%2, %3};\n"
+        "mov.b64 rb, {%4, %5};\n"
+        "mov.b64 rc, {%6, %7};\n"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n"
+        "mov.b64 {%0, %1}, rd;\n"
+        "}\n" : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ void zero_acc2(Acc2& a) {
+#pragma unroll
+    for (int i = 0; i < 18; i++) a.p[i] = make_float2(0.f, 0.f);
+    a.dd = make_float2(0.f, 0.f); a.dz2 = 0.f; a.cnt = 0.f;
+}
+__device__ __forceinline__ void accumulate2(Acc2& a, float px, float py, float pz, const Corr& c) {
+    const float dx = c.qx - px, dy = c.qy - py, dz = c.qz - pz;
+    const float r = dx * c.nx + dy * c.ny + dz * c.nz;
+    const float2 E0 = make_float2(c.nz * py - c.ny * pz, c.nx * pz - c.nz * px);
+    const float2 E1 = make_float2(c.ny * px - c.nx * py, c.nx);
+    const float2 E2 = make_float2(c.ny, c.nz);
+    const float2 E3 = make_float2(r, 0.f);
+    a.p[0] = ffma2(E0.x, E0, a.p[0]); a.p[1] = ffma2(E0.x, E1, a.p[1]); a.p[2] = ffma2(E0.x, E2, a.p[2]); a.p[3] = ffma2(E0.x, E3, a.p[3]);
+    a.p[4] = ffma2(E0.y, E0, a.p[4]); a.p[5] = ffma2(E0.y, E1, a.p[5]); a.p[6] = ffma2(E0.y, E2, a.p[6]); a.p[7] = ffma2(E0.y, E3, a.p[7]);
+    a.p[8] = ffma2(E1.x, E1, a.p[8]); a.p[9] = ffma2(E1.x, E2, a.p[9]); a.p[10] = ffma2(E1.x, E3, a.p[10]);
+    a.p[11] = ffma2(E1.y, E1, a.p[11]); a.p[12] = ffma2(E1.y, E2, a.p[12]); a.p[13] = ffma2(E1.y, E3, a.p[13]);
+    a.p[14] = ffma2(E2.x, E2, a.p[14]); a.p[15] = ffma2(E2.x, E3, a.p[15]);
+    a.p[16] = ffma2(E2.y, E2, a.p[16]); a.p[17] = ffma2(E2.y, E3, a.p[17]);
+    a.dd = ffma2v(make_float2(dx, dy), make_float2(dx, dy), a.dd);
+    a.dz2 = fmaf(dz, dz, a.dz2);
+    a.cnt += 1.0f;
+}
+// packed slots -> the 29 sums in thrust__pcd2Ab's order (icp.h:165-206), padded to 32
+__device__ __forceinline__ void unpack_acc2(const Acc2& a, float (&v)[32]) {
+    v[0] = a.p[0].x;  v[1] = a.p[0].y;  v[2] = a.p[1].x;  v[3] = a.p[1].y;  v[4] = a.p[2].x;  v[5] = a.p[2].y;   // J0 * J0..J5
+    v[6] = a.p[4].y;  v[7] = a.p[5].x;  v[8] = a.p[5].y;  v[9] = a.p[6].x;  v[10] = a.p[6].y;                    // J1 * J1..J5
+    v[11] = a.p[8].x; v[12] = a.p[8].y; v[13] = a.p[9].x; v[14] = a.p[9].y;                                      // J2 * J2..J5
+    v[15] = a.p[11].y; v[16] = a.p[12].x; v[17] = a.p[12].y;                                                     // J3 * J3..J5
+    v[18] = a.p[14].x; v[19] = a.p[14].y;                                                                        // J4 * J4..J5
+    v[20] = a.p[16].y;                                                                                           // J5 * J5
+    v[21] = a.p[3].x; v[22] = a.p[7].x; v[23] = a.p[10].x; v[24] = a.p[13].x; v[25] = a.p[15].x; v[26] = a.p[17].x;   // J * r
+    v[27] = a.dd.x + a.dd.y + a.dz2;
+    v[28] = a.cnt;
+    v[29] = 0.f; v[30] = 0.f; v[31] = 0.f;
+}
+
+struct Acc1 { float v[32]; };     // scalar accumulation: one FFMA per sum (first generation)
+__device__ __forceinline__ void acc_zero(Acc1& a) {
+#pragma unroll
+    for (int i = 0; i < 32; i++) a.v[i] = 0.f;
+}
+__device__ __forceinline__ void acc_zero(Acc2& a) { zero_acc2(a); }
+__device__ __forceinline__ void acc_add(Acc1& a, float px, float py, float pz, const Corr& c) { accumulate(a.v, px, py, pz, c); }
+__device__ __forceinline__ void acc_add(Acc2& a, float px, float py, float pz, const Corr& c) { accumulate2(a, px, py, pz, c); }
+__device__ __forceinline__ void acc_unpack(const Acc1& a, float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = a.v[i];
+}
+__device__ __forceinline__ void acc_unpack(const Acc2& a, float (&v)[32]) { unpack_acc2(a, v); }
+#ifndef PR_FFMA2
+#define PR_FFMA2 1
+#endif
+#if PR_FFMA2
+typedef Acc2 AccT;
+#else
+typedef Acc1 AccT;
+#endif
+
 // Warp reduction of 32 values per lane that leaves, in lane L, the warp-wide sum of value L:
 // at each butterfly step a lane keeps one half of its values and ships the other half, so the
 // whole thing costs 16+8+4+2+1 = 31 shuffles instead of 32*5.
@@ -637,7 +729,7 @@ __device__ __forceinline__ float fast_rcp(float z) {
 // rejected value (a plain float->int conversion would turn NaN into pixel 0).
 template <bool TAIL>
 __device__ __forceinline__ void group_projective(const PackedScene& s, unsigned addr, unsigned first, unsigned n,
-                                                 const float* T, float* acc) {
+                                                 const float* T, AccT& acc) {
     float px[kIlp], py[kIlp], pz[kIlp];
     int idx[kIlp];
     bool ok[kIlp];
@@ -667,18 +759,19 @@ __device__ __forceinline__ void group_projective(const PackedScene& s, unsigned 
             if (A[k].z > 0.f && fabsf(pz[k] - A[k].z) <= s.max_dist) {       // depth_scene.h:42
                 Corr cr;
                 cr.qx = A[k].x; cr.qy = A[k].y; cr.qz = A[k].z; cr.nx = A[k].w; cr.ny = B[k].x; cr.nz = B[k].y;
-                accumulate(acc, px[k], py[k], pz[k], cr);
+                acc_add(acc, px[k], py[k], pz[k], cr);
             }
         }
     }
 }
 
 // one warp tile (n <= kWTile points at shared address `tile`), packed projective scene
-__device__ __forceinline__ void compute_tile(const PackedScene& s, unsigned tile, unsigned n, const float* T, float* acc) {
+__device__ __forceinline__ void compute_tile(const PackedScene& s, unsigned tile, unsigned n, const float* T, AccT& acc) {
     const unsigned lane = threadIdx.x & 31;
     unsigned addr = tile + 12 * lane;
     unsigned first = lane;                         // index of this lane's first point in the group
     constexpr unsigned kGroup = 32 * kIlp;
+    static_assert(kWTile % kGroup == 0, "a tail group must not read past the tile");
     const unsigned n_full = n - n % kGroup;
 #pragma unroll 1
     for (; first < n_full; first += kGroup, addr += 12 * kGroup) group_projective<false>(s, addr, first, n, T, acc);
@@ -687,14 +780,14 @@ __device__ __forceinline__ void compute_tile(const PackedScene& s, unsigned tile
 
 // one warp tile, any scene with a per-point query() (nearest neighbour)
 template <class SceneT>
-__device__ __forceinline__ void compute_tile(const SceneT& s, unsigned tile, unsigned n, const float* T, float* acc) {
+__device__ __forceinline__ void compute_tile(const SceneT& s, unsigned tile, unsigned n, const float* T, AccT& acc) {
     const unsigned lane = threadIdx.x & 31;
 #pragma unroll 1
     for (unsigned i = lane; i < n; i += 32) {
         float px, py, pz;
         transform(T, lds32(tile + 12 * i), lds32(tile + 12 * i + 4), lds32(tile + 12 * i + 8), px, py, pz);
         Corr c;
-        if (query(s, px, py, pz, c)) accumulate(acc, px, py, pz, c);
+        if (query(s, px, py, pz, c)) acc_add(acc, px, py, pz, c);
     }
 }
 
@@ -801,11 +894,10 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
         }
         const bool skip = __shfl_sync(0xffffffffu, flag, 0) != 0;
         float T[12];
-        float acc[32];
+        AccT acc;
 #pragma unroll
         for (int i = 0; i < 12; i++) T[i] = skip ? 0.f : __ldcg(&st->T[i]);
-#pragma unroll
-        for (int i = 0; i < 32; i++) acc[i] = 0.f;
+        acc_zero(acc);
 
         unsigned next_item = 0xFFFFFFFFu;
         const float* next_g = pts;
@@ -837,7 +929,9 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
 
         // ---- item complete: reduce over the warp, deposit, maybe finish the pass of this hypothesis
         if (!skip) {
-            const float mine = warp_transpose_reduce(acc);     // lane l = sum of value l
+            float v[32];
+            acc_unpack(acc, v);
+            const float mine = warp_transpose_reduce(v);       // lane l = sum of value l
             __stcg(partials + (size_t)c * kPartialStride + lane, mine);
             __syncwarp();            // all 32 partial stores precede lane 0's release below
             int is_last = 0;

@@ -4,4 +4,4 @@ mkdir -p gpurun_out
 for f in pose_refine_b200/variants/lib_*.so; do
   PR_LIB=$PWD/$f timeout 200 python scripts/time_icp.py 512 8 >> gpurun_out/variants.jsonl 2>> gpurun_out/variants.err
 done
-cat gpurun_out/variants.jsonl; tail -3 gpurun_out/variants.err
+cat gpurun_out/variants.jsonl; grep -iE "error|assert" gpurun_out/variants.err | sort | uniq -c | head -5
