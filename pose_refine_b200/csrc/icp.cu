@@ -480,7 +480,8 @@ __device__ __forceinline__ void finish_pass_release(HypState* st, const float* S
 __global__ void __launch_bounds__(kIcpThreads)
 icp_plan_kernel(const uint32_t* __restrict__ counts, uint32_t n_hyp, uint32_t chunk_points, HypState* __restrict__ state,
                 uint32_t* __restrict__ chunk_hyp, uint32_t max_chunks, uint32_t* __restrict__ total_chunks,
-                pr_registration_result* __restrict__ results, unsigned* __restrict__ next_item) {
+                pr_registration_result* __restrict__ results, unsigned* __restrict__ next_item,
+                const uint32_t* __restrict__ offsets = nullptr, uint4* __restrict__ chunk_info = nullptr) {
     __shared__ unsigned s_warp[kIcpWarps];
     __shared__ unsigned s_carry;
     if (threadIdx.x == 0) s_carry = 0;
@@ -514,7 +515,14 @@ icp_plan_kernel(const uint32_t* __restrict__ counts, uint32_t n_hyp, uint32_t ch
             for (int i = 0; i < 16; i++) r.transformation[i] = (i % 5 == 0) ? 1.f : 0.f;
             r.inlier_rmse = 0.f; r.fitness = 0.f;
             results[h] = r;
-            for (unsigned j = 0; j < v; j++) if (begin + j < max_chunks) chunk_hyp[begin + j] = h;
+            const unsigned off = chunk_info ? offsets[h] : 0u;
+            for (unsigned j = 0; j < v; j++) {
+                if (begin + j >= max_chunks) break;
+                chunk_hyp[begin + j] = h;
+                // everything a worker needs to know about a chunk in one 16-byte record:
+                // hypothesis, first point (absolute), number of points, points of the hypothesis
+                if (chunk_info) chunk_info[begin + j] = make_uint4(h, off + j * chunk_points, min(chunk_points, cnt - j * chunk_points), cnt);
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) s_carry += all;
@@ -830,8 +838,7 @@ __device__ __forceinline__ bool stage_tile(const float* src, unsigned n, uintptr
 
 template <class SceneT>
 __global__ void __launch_bounds__(kPThreads, PR_MINB)
-icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, const uint32_t* __restrict__ offsets,
-                      const uint32_t* __restrict__ counts, const uint32_t* __restrict__ chunk_hyp, IcpCtl* ctl,
+icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, const uint4* __restrict__ chunk_info, IcpCtl* ctl,
                       HypState* state, float* partials, SceneT scene, pr_icp_criteria crit,
                       pr_registration_result* results) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -854,32 +861,28 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
         if (lane == 0) v = atomicAdd(&ctl->next_item, 1u);
         return __shfl_sync(0xffffffffu, v, 0);
     };
-    // item -> (first point pointer, number of points)
-    auto locate = [&](unsigned item, const float*& g, unsigned& n_pts) {
-        const unsigned pass = item / total;
-        const unsigned c = item - pass * total;
-        const unsigned h = __ldg(chunk_hyp + c);
-        const unsigned first = (c - __ldcg(&state[h].chunk_begin)) * kPersistChunk;
-        n_pts = min(kPersistChunk, __ldg(counts + h) - first);
-        g = pts + 3 * ((size_t)__ldg(offsets + h) + first);
+    // item -> its chunk record {hypothesis, first point, points in chunk, points of the hypothesis}
+    auto locate = [&](unsigned item) {
+        const unsigned c = item % total;
+        return (item < n_items) ? __ldg(chunk_info + c) : make_uint4(0u, 0u, 0u, 0u);
     };
 
     unsigned stage = 0;                 // stage that holds (or will hold) the next tile to consume
     unsigned parity = 0;                // bit s = parity to wait for on stage s
     unsigned item = claim();
-    const float* g = pts;
-    unsigned n_pts = 0;
+    uint4 info = locate(item);
     bool tma_cur = false;               // was the next tile to consume fetched by TMA?
-    if (item < n_items) {
-        locate(item, g, n_pts);
-        tma_cur = stage_tile(g, min((unsigned)kWTile, n_pts), pts_end, tile0 + stage * kWTileBytes, bar0 + 8 * stage);
-    }
+    if (item < n_items)
+        tma_cur = stage_tile(pts + 3 * (size_t)info.y, min((unsigned)kWTile, info.z), pts_end, tile0 + stage * kWTileBytes, bar0 + 8 * stage);
     while (item < n_items) {
         const unsigned pass = item / total;
         const unsigned c = item - pass * total;
-        const unsigned h = __ldg(chunk_hyp + c);
+        const unsigned h = info.x, n_pts = info.z;
+        const float* g = pts + 3 * (size_t)info.y;
         HypState* st = state + h;
         const unsigned n_tiles = (n_pts + kWTile - 1) / kWTile;
+        unsigned next_item = 0xFFFFFFFFu;
+        uint4 next_info = make_uint4(0u, 0u, 0u, 0u);
 
         // ---- wait until the hypothesis has finished the previous pass (or has returned)
         int flag = 0;
@@ -899,9 +902,6 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
         for (int i = 0; i < 12; i++) T[i] = skip ? 0.f : __ldcg(&st->T[i]);
         acc_zero(acc);
 
-        unsigned next_item = 0xFFFFFFFFu;
-        const float* next_g = pts;
-        unsigned next_n = 0;
         for (unsigned t = 0; t < n_tiles; t++) {
             // ---- prefetch: next tile of this item, or the first tile of the next claimed item
             bool tma_next = false;
@@ -910,11 +910,13 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
                 tma_next = stage_tile(g + (size_t)(t + 1) * kWTileFloats, min((unsigned)kWTile, n_pts - (t + 1) * kWTile), pts_end,
                                       tile0 + other * kWTileBytes, bar0 + 8 * other);
             } else {
+                // claim the next item only now: claiming earlier parks ~1 item per warp in front of the
+                // workers, which pushes them a pass ahead of their dependencies (measured: 2.21 -> 2.33 ms)
                 next_item = claim();
-                if (next_item < n_items) {
-                    locate(next_item, next_g, next_n);
-                    tma_next = stage_tile(next_g, min((unsigned)kWTile, next_n), pts_end, tile0 + other * kWTileBytes, bar0 + 8 * other);
-                }
+                next_info = locate(next_item);
+                if (next_item < n_items)
+                    tma_next = stage_tile(pts + 3 * (size_t)next_info.y, min((unsigned)kWTile, next_info.z), pts_end,
+                                          tile0 + other * kWTileBytes, bar0 + 8 * other);
             }
             // ---- consume tile t
             if (tma_cur) {
@@ -937,11 +939,10 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
             int is_last = 0;
             if (lane == 0) is_last = (atom_add_release(&st->arrived, 1u) == __ldcg(&st->n_chunks) - 1) ? 1 : 0;
             is_last = __shfl_sync(0xffffffffu, is_last, 0);
-            if (is_last) warp_finish_hypothesis(st, partials, __ldg(counts + h), crit, results + h);
+            if (is_last) warp_finish_hypothesis(st, partials, info.w, crit, results + h);
         }
         item = next_item;
-        g = next_g;
-        n_pts = next_n;
+        info = next_info;
     }
 }
 
@@ -973,7 +974,7 @@ icp_apply_kernel(float* __restrict__ pts, const uint32_t* __restrict__ offsets, 
 inline size_t icp_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct IcpWs {
-    HypState* state; uint32_t* chunk_hyp; IcpCtl* ctl; float* partials; float4* packed; float2* packed2;
+    HypState* state; uint32_t* chunk_hyp; uint4* chunk_info; IcpCtl* ctl; float* partials; float4* packed; float2* packed2;
     size_t max_chunks, bytes;
 };
 
@@ -994,6 +995,7 @@ inline IcpWs carve_icp_ws(void* base, size_t n_hyp, size_t capacity_points, size
     auto take = [&](size_t bytes) { char* p = w + used; used += icp_align_up(bytes, 256); return p; };
     ws.state = (HypState*)take(n_hyp * sizeof(HypState));
     ws.chunk_hyp = (uint32_t*)take(ws.max_chunks * 4);
+    ws.chunk_info = (uint4*)take(ws.max_chunks * 16);
     ws.ctl = (IcpCtl*)take(sizeof(IcpCtl));
     ws.partials = (float*)take(ws.max_chunks * kPartialStride * 4);
     ws.packed = (float4*)take(scene_pixels * 16);
@@ -1050,13 +1052,14 @@ int run_icp(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_
     const size_t max_items = (capacity_points / kPersistChunk + n_hyp + 1) * (size_t)(crit.max_iteration + 1);
     if (max_items > 0x7FFFFFFFull) return PR_ERR_INVALID_ARGUMENT;
     icp_plan_kernel<<<1, kIcpThreads, 0, stream>>>(counts_dev, (uint32_t)n_hyp, kPersistChunk, ws.state, ws.chunk_hyp,
-                                                   (uint32_t)ws.max_chunks, &ws.ctl->total_chunks, results_dev, &ws.ctl->next_item);
+                                                   (uint32_t)ws.max_chunks, &ws.ctl->total_chunks, results_dev, &ws.ctl->next_item,
+                                                   offsets_dev, ws.chunk_info);
     int grid = 0;
     int rc = persistent_grid<PScene>(&grid);
     if (rc != PR_OK) return rc;
     grid = (int)std::min<size_t>((size_t)grid, (max_items + kPWarps - 1) / kPWarps);
     icp_persistent_kernel<PScene><<<grid, kPThreads, kPersistSmem, stream>>>(
-        pts_dev, capacity_points, offsets_dev, counts_dev, ws.chunk_hyp, ws.ctl, ws.state, ws.partials, pscene, crit, results_dev);
+        pts_dev, capacity_points, ws.chunk_info, ws.ctl, ws.state, ws.partials, pscene, crit, results_dev);
     count_launch(2);
     if (flags & PR_ICP_UPDATE_POINTS) {
         icp_apply_kernel<<<kNumSMs * 4, 256, 0, stream>>>(pts_dev, offsets_dev, counts_dev, ws.chunk_hyp, &ws.ctl->total_chunks,
