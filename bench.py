@@ -306,8 +306,13 @@ def run_ours(args):
         bytes_per_launch = passes * bytes_per_pass
         peak, peak_src = measured_peaks()
         achieved = bytes_per_launch / (ms_icp * 1e-3) / 1e9
+        traffic = None     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
+        tp = os.path.join(ROOT, "profiles", "r01_icp_traffic.json")
+        if os.path.exists(tp) and P == 512:
+            with open(tp) as f:
+                traffic = json.load(f)["traffic_bytes_per_launch"]
         roofline = {"bound": "hbm", "kernel": "icp_persistent_kernel<PackedScene> (one launch = 31 passes over all hypotheses)",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": ms_icp,
                     "note": "launch_ms = CUDA-event time of pr_icp_projective_batch (scene pack 5 us + plan 13 us + the persistent kernel)"}
         stage = {"render_ms": ms_render, "depth2cloud_ms": ms_cloud, "icp_ms": ms_icp, "model_points": n_pts,
