@@ -119,6 +119,17 @@ int pr_render_batch(const float* tris_dev, size_t n_tris, const float* poses, in
                     size_t width, size_t height, const float proj[16], pr_roi roi, int32_t* out_depth_dev,
                     void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
 
+/* Indexed variant (no upstream counterpart: the reference renders a triangle soup).  Unique vertices are  */
+/* projected once per pose, so a triangle's setup is three 16-byte loads instead of six transforms and six   */
+/* divisions; the result is bit-identical to pr_render_batch.  pr_mesh_index (host) deduplicates a soup:      */
+/* verts_out has room for 3*n_tris vertices (pass NULL to count), faces_out for 3*n_tris indices.            */
+int pr_mesh_index(const float* tris_host, size_t n_tris, float* verts_out, int32_t* faces_out, size_t* n_verts);
+size_t pr_render_indexed_workspace_bytes(size_t n_poses, size_t n_verts, size_t n_tris, size_t width, size_t height);
+int pr_render_indexed_batch(const float* verts_dev, size_t n_verts, const int32_t* faces_dev, size_t n_tris,
+                            const float* poses, int poses_on_device, size_t n_poses, size_t width, size_t height,
+                            const float proj[16], pr_roi roi, int32_t* out_depth_dev,
+                            void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
+
 /* raw2depth_uint16_cuda / raw2mask_uint8_cuda / raw2depth_mask_cuda (renderer.cu:338-439):      */
 /* depth = uint16_t(raw), mask = raw > 0 ? 255 : 0.  Either output may be NULL.                  */
 int pr_raw2depth_mask(const int32_t* raw_dev, size_t n, uint16_t* depth_dev, uint8_t* mask_dev, pr_stream_t stream);

@@ -139,6 +139,35 @@ def render_cuda_keep_in_gpu(tris, poses, width, height, proj_mat, roi=(0, 0, 0, 
     return out
 
 
+def mesh_index(tris):
+    """Deduplicate a triangle soup [T,9] -> (vertices [V,3] float32, faces [T,3] int32) (pr_mesh_index, host)."""
+    tris = _f32c(tris).reshape(-1, 9)
+    n = C.c_size_t()
+    verts = np.zeros((tris.shape[0] * 3, 3), np.float32)
+    faces = np.zeros((tris.shape[0], 3), np.int32)
+    check(lib().pr_mesh_index(tris.ctypes.data, tris.shape[0], verts.ctypes.data, faces.ctypes.data, C.byref(n)), "pr_mesh_index")
+    return verts[: n.value].copy(), faces
+
+
+def render_indexed_keep_in_gpu(verts, faces, poses, width, height, proj_mat, roi=(0, 0, 0, 0)):
+    """Indexed-mesh variant of render_cuda_keep_in_gpu: same output, vertices projected once per pose."""
+    _require_device()
+    verts = _dev(verts, torch.float32).reshape(-1, 3)
+    faces = _dev(faces, torch.int32).reshape(-1, 3)
+    proj = _f32c(proj_mat).reshape(16)
+    roi_c = _lib.Roi(*[int(v) for v in roi])
+    rw, rh = (roi_c.width, roi_c.height) if roi_c.width > 0 and roi_c.height > 0 else (width, height)
+    poses_t = _dev(poses, torch.float32).reshape(-1, 16)
+    n_poses = poses_t.shape[0]
+    out = torch.empty((n_poses, rh, rw), dtype=torch.int32, device="cuda")
+    ws_bytes = lib().pr_render_indexed_workspace_bytes(n_poses, verts.shape[0], faces.shape[0], width, height)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    check(lib().pr_render_indexed_batch(verts.data_ptr(), verts.shape[0], faces.data_ptr(), faces.shape[0], poses_t.data_ptr(), 1,
+                                        n_poses, width, height, proj.ctypes.data, roi_c, out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                        _stream()), "pr_render_indexed_batch")
+    return out
+
+
 def render_cuda(tris, poses, width, height, proj_mat, roi=(0, 0, 0, 0)):
     """-> host int32 array (renderer.cu:189-267)."""
     return render_cuda_keep_in_gpu(tris, poses, width, height, proj_mat, roi).cpu().numpy()

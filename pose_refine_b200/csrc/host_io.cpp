@@ -135,6 +135,37 @@ int pr_load_ply(const char* path, float* tris_host, size_t capacity_tris, size_t
     return PR_OK;
 }
 
+int pr_mesh_index(const float* tris_host, size_t n_tris, float* verts_out, int32_t* faces_out, size_t* n_verts) {
+    if (!tris_host || !faces_out || !n_verts) return PR_ERR_INVALID_ARGUMENT;
+    // exact-bit deduplication of the 3*n_tris corners (open addressing on the 96-bit pattern)
+    const size_t n_corners = n_tris * 3;
+    size_t cap = 16;
+    while (cap < n_corners * 2) cap <<= 1;
+    std::vector<int32_t> table(cap, -1);
+    std::vector<float> verts;
+    verts.reserve(n_corners);
+    for (size_t c = 0; c < n_corners; c++) {
+        uint32_t k[3];
+        memcpy(k, tris_host + 3 * c, 12);
+        uint64_t h = (k[0] * 0x9E3779B97F4A7C15ull) ^ (k[1] * 0xC2B2AE3D27D4EB4Full) ^ (k[2] * 0x165667B19E3779F9ull);
+        size_t slot = (size_t)(h >> 20) & (cap - 1);
+        for (;;) {
+            const int32_t v = table[slot];
+            if (v < 0) {
+                table[slot] = (int32_t)(verts.size() / 3);
+                verts.insert(verts.end(), tris_host + 3 * c, tris_host + 3 * c + 3);
+                faces_out[c] = table[slot];
+                break;
+            }
+            if (memcmp(verts.data() + 3 * (size_t)v, k, 12) == 0) { faces_out[c] = v; break; }
+            slot = (slot + 1) & (cap - 1);
+        }
+    }
+    *n_verts = verts.size() / 3;
+    if (verts_out) memcpy(verts_out, verts.data(), verts.size() * 4);
+    return PR_OK;
+}
+
 int pr_compute_proj(const float K[9], int width, int height, float near_plane, float far_plane, float p[16]) {
     if (!K || !p || width <= 0 || height <= 0) return PR_ERR_INVALID_ARGUMENT;
     for (int i = 0; i < 16; i++) p[i] = 0.f;

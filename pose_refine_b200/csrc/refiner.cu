@@ -20,6 +20,9 @@ struct pr_refiner {
     float proj[16];
     size_t n_tris = 0, max_hyp = 0, capacity_points = 0;
     float* d_tris = nullptr;
+    float* d_verts = nullptr;     // deduplicated mesh (pr_mesh_index): the refiner renders the indexed form
+    int32_t* d_faces = nullptr;
+    size_t n_verts = 0;
     float* d_poses = nullptr;
     int32_t* d_depth = nullptr;
     float* d_pts = nullptr;
@@ -49,8 +52,8 @@ int run_device(pr_refiner* r, const float* poses_dev, size_t n_hyp, pr_icp_crite
                pr_registration_result* results_dev, cudaStream_t stream) {
     pr_stream_t s = reinterpret_cast<pr_stream_t>(stream);
     pr_roi none = {0, 0, 0, 0};
-    int rc = pr_render_batch(r->d_tris, r->n_tris, poses_dev, 1, n_hyp, r->W, r->H, r->proj, none, r->d_depth,
-                             r->ws_render, r->ws_render_bytes, s);
+    int rc = pr_render_indexed_batch(r->d_verts, r->n_verts, r->d_faces, r->n_tris, poses_dev, 1, n_hyp, r->W, r->H, r->proj, none,
+                                     r->d_depth, r->ws_render, r->ws_render_bytes, s);
     if (rc != PR_OK) return rc;
     rc = pr_depth2cloud_count(r->d_depth, 1, n_hyp, r->W, r->H, 1, 4, r->capacity_points, r->d_counts, r->d_offsets,
                               r->d_overflow, r->ws_cloud, r->ws_cloud_bytes, s);
@@ -132,12 +135,18 @@ int pr_refiner_create(pr_refiner** out, const float* tris_host, size_t n_tris, u
     const size_t n_px = (size_t)width * height;
     // default: room for every hypothesis covering a quarter of the image
     r->capacity_points = capacity_points ? capacity_points : (max_hyp * (n_px / 4 + 4));
-    r->ws_render_bytes = pr_render_workspace_bytes(max_hyp, n_tris, width, height);
+    std::vector<float> verts(n_tris * 9);
+    std::vector<int32_t> faces(n_tris * 3);
+    rc = pr_mesh_index(tris_host, n_tris, verts.data(), faces.data(), &r->n_verts);
+    if (rc != PR_OK) { delete r; return rc; }
+    r->ws_render_bytes = pr_render_indexed_workspace_bytes(max_hyp, r->n_verts, n_tris, width, height);
     r->ws_cloud_bytes = pr_depth2cloud_workspace_bytes(max_hyp, width, height);
     r->ws_icp_bytes = pr_icp_workspace_bytes(max_hyp, r->capacity_points, 3 * n_px + 16);   // projective: n_px; kd-tree: <= n_px points + 2 * (2 n_px + 1) nodes... bounded by 3 n_px for leaf >= 2
     cudaError_t e = cudaSuccess;
     auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 256); };
     alloc((void**)&r->d_tris, n_tris * 36);
+    alloc((void**)&r->d_verts, r->n_verts * 12);
+    alloc((void**)&r->d_faces, n_tris * 12);
     alloc((void**)&r->d_poses, max_hyp * 64);
     alloc((void**)&r->d_depth, max_hyp * n_px * 4);
     alloc((void**)&r->d_pts, r->capacity_points * 12 + 64);
@@ -150,6 +159,8 @@ int pr_refiner_create(pr_refiner** out, const float* tris_host, size_t n_tris, u
     alloc(&r->ws_icp, r->ws_icp_bytes);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&r->h_overflow, 256);
     if (e == cudaSuccess) e = cudaMemcpy(r->d_tris, tris_host, n_tris * 36, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_verts, verts.data(), r->n_verts * 12, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_faces, faces.data(), n_tris * 12, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(r->d_overflow, 0, 256);
     if (e != cudaSuccess) { pr_refiner_destroy(r); return (int)e; }
     *out = r;
@@ -159,7 +170,7 @@ int pr_refiner_create(pr_refiner** out, const float* tris_host, size_t n_tris, u
 void pr_refiner_destroy(pr_refiner* r) {
     if (!r) return;
     free_scene(r);
-    cudaFree(r->d_tris); cudaFree(r->d_poses); cudaFree(r->d_depth); cudaFree(r->d_pts);
+    cudaFree(r->d_tris); cudaFree(r->d_verts); cudaFree(r->d_faces); cudaFree(r->d_poses); cudaFree(r->d_depth); cudaFree(r->d_pts);
     cudaFree(r->d_counts); cudaFree(r->d_offsets); cudaFree(r->d_overflow); cudaFree(r->d_results);
     cudaFree(r->ws_render); cudaFree(r->ws_cloud); cudaFree(r->ws_icp);
     if (r->h_overflow) cudaFreeHost(r->h_overflow);

@@ -96,6 +96,28 @@ def test_render_sphere_behind_camera_and_empty(api, port, golden):
     assert api.render_cuda_keep_in_gpu(tris, np.zeros((0, 4, 4), np.float32), 640, 480, arrays["proj"]).shape[0] == 0
 
 
+def test_render_indexed_mesh_bit_exact(api, port, mesh, golden):
+    """The indexed-mesh rasteriser (what pr_refiner uses) renders the same images as the soup path and the oracle."""
+    arrays, scal = golden
+    verts, faces = api.mesh_index(mesh)
+    assert verts.shape[0] == 15736 and faces.shape == (31468, 3)            # obj_06: 15,736 unique vertices
+    assert np.array_equal(verts[faces.reshape(-1)].reshape(-1, 9), mesh)
+    d = api.render_indexed_keep_in_gpu(verts, faces, arrays["hyp8"], 640, 480, arrays["proj"]).cpu().numpy()
+    assert [crc(x) for x in d] == [g["crc"] for g in scal["render_hyp8"]]
+    d = api.render_indexed_keep_in_gpu(verts, faces, arrays["poses"], 640, 480, arrays["proj"], wl.ROI_FIXTURE).cpu().numpy()
+    assert [crc(x) for x in d] == [g["crc"] for g in scal["render_roi"]]
+    d = api.render_indexed_keep_in_gpu(verts, faces, arrays["pose_near"][None], 640, 480, arrays["proj"]).cpu().numpy()
+    assert crc(d[0]) == scal["render_near"]["crc"]
+    d = api.render_indexed_keep_in_gpu(verts, faces, arrays["poses"], 161, 121, arrays["proj_small"], (33, 17, 71, 53)).cpu().numpy()
+    assert [crc(x) for x in d] == [g["crc"] for g in scal["render_small_roi"]]
+    tris = wl.uv_sphere(50.0, 40, 37)
+    sv, sf = api.mesh_index(tris)
+    poses = wl.shoemake_poses(3, seed=5)
+    poses[2, 2, 3] = 30.0
+    got = api.render_indexed_keep_in_gpu(sv, sf, poses, 640, 480, arrays["proj"]).cpu().numpy()
+    assert np.array_equal(got, port.render(tris, poses, 640, 480, arrays["proj"]))
+
+
 def test_render_big_triangles_overflowing_bins(api, port, golden):
     """A few screen-filling triangles: every tile lists them; the per-pose list capacity still holds,
     and with a deliberately tiny workspace the overflow fallback must give the same image."""
