@@ -258,7 +258,7 @@ __device__ __forceinline__ bool query(const PackedNnScene& s, float px, float py
 }
 
 // thrust__pcd2Ab::operator() (icp.h:138-208): adds one correspondence into the 29 running sums.
-__device__ __forceinline__ void accumulate(float* acc, float px, float py, float pz, const Corr& c) {
+__device__ __forceinline__ void accumulate(float* acc, float px, float py, float pz, const Corr& c, float w = 1.0f) {
     const float dx = c.qx - px, dy = c.qy - py, dz = c.qz - pz;
     const float r = dx * c.nx + dy * c.ny + dz * c.nz;
     float J[6];
@@ -274,7 +274,7 @@ __device__ __forceinline__ void accumulate(float* acc, float px, float py, float
 #pragma unroll
     for (int i = 0; i < 6; i++) acc[21 + i] = fmaf(J[i], r, acc[21 + i]);
     acc[27] += dx * dx + dy * dy + dz * dz;
-    acc[28] += 1.0f;
+    acc[28] += w;
 }
 
 // ---- packed accumulation (sm_100 FFMA2) ------------------------------------------------------------
@@ -316,7 +316,7 @@ __device__ __forceinline__ void zero_acc2(Acc2& a) {
     for (int i = 0; i < 18; i++) a.p[i] = make_float2(0.f, 0.f);
     a.dd = make_float2(0.f, 0.f); a.dz2 = 0.f; a.cnt = 0.f;
 }
-__device__ __forceinline__ void accumulate2(Acc2& a, float px, float py, float pz, const Corr& c) {
+__device__ __forceinline__ void accumulate2(Acc2& a, float px, float py, float pz, const Corr& c, float w = 1.0f) {
     const float dx = c.qx - px, dy = c.qy - py, dz = c.qz - pz;
     const float r = dx * c.nx + dy * c.ny + dz * c.nz;
     const float2 E0 = make_float2(c.nz * py - c.ny * pz, c.nx * pz - c.nz * px);
@@ -331,7 +331,7 @@ __device__ __forceinline__ void accumulate2(Acc2& a, float px, float py, float p
     a.p[16] = ffma2(E2.y, E2, a.p[16]); a.p[17] = ffma2(E2.y, E3, a.p[17]);
     a.dd = ffma2v(make_float2(dx, dy), make_float2(dx, dy), a.dd);
     a.dz2 = fmaf(dz, dz, a.dz2);
-    a.cnt += 1.0f;
+    a.cnt += w;
 }
 // packed slots -> the 29 sums in thrust__pcd2Ab's order (icp.h:165-206), padded to 32
 __device__ __forceinline__ void unpack_acc2(const Acc2& a, float (&v)[32]) {
@@ -345,6 +345,61 @@ __device__ __forceinline__ void unpack_acc2(const Acc2& a, float (&v)[32]) {
     v[27] = a.dd.x + a.dd.y + a.dz2;
     v[28] = a.cnt;
     v[29] = 0.f; v[30] = 0.f; v[31] = 0.f;
+}
+
+
+// ---- two points per instruction ---------------------------------------------------------------------
+// The second generation of the packed path: instead of packing two SUMS of one point into an FFMA2
+// (which needs register moves to form the operand pairs), every quantity of the point pipeline is a
+// pair (value for point A, value for point B) of the two points a lane processes together --
+// transform, projection, residual, Jacobian and all 29 sums run as FFMA2 / FMUL2 / FADD2 with no
+// packing moves: the per-point selects that reject a correspondence write straight into the halves of
+// the pair registers.  Sum i is kept as (sum over "A" points, sum over "B" points) and folded at the end
+// of the item.  Pairs are carried as 64-bit values so that ptxas allocates them as aligned register
+// pairs once; it folds negation and scalar broadcast into the FFMA2 operands.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk2(float lo, float hi) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2_t bc2(float a) { return pk2(a, a); }
+__device__ __forceinline__ void unpk2(f2_t a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); }
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) { f2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) { f2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2_t sub2(f2_t a, f2_t b) { f2_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2_t neg2(f2_t a) {
+    f2_t d;
+    asm("{\n.reg .f32 l, h;\nmov.b64 {l, h}, %1;\nneg.f32 l, l;\nneg.f32 h, h;\nmov.b64 %0, {l, h};\n}" : "=l"(d) : "l"(a));
+    return d;
+}
+struct AccP { f2_t s[28]; float cnt_a, cnt_b; };   // s[i] = Vec29f entry i (icp.h:165-206) as (sum over A points, sum over B points)
+__device__ __forceinline__ void acc_zero(AccP& a) {
+#pragma unroll
+    for (int i = 0; i < 28; i++) a.s[i] = pk2(0.f, 0.f);
+    a.cnt_a = 0.f; a.cnt_b = 0.f;
+}
+__device__ __forceinline__ void acc_unpack(const AccP& a, float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 28; i++) { float lo, hi; unpk2(a.s[i], lo, hi); v[i] = lo + hi; }
+    v[28] = a.cnt_a + a.cnt_b;
+    v[29] = 0.f; v[30] = 0.f; v[31] = 0.f;
+}
+// thrust__pcd2Ab::operator() (icp.h:138-208) for two points at once; a rejected point arrives as q = p, n = 0
+// (so d = 0, r = 0, J = 0: all 28 float sums get +0); the caller counts the accepted points.
+__device__ __forceinline__ void accumulate_pair(AccP& a, f2_t px, f2_t py, f2_t pz, f2_t qx, f2_t qy, f2_t qz,
+                                                f2_t nx, f2_t ny, f2_t nz) {
+    const f2_t dx = sub2(qx, px), dy = sub2(qy, py), dz = sub2(qz, pz);
+    const f2_t r = fma2(dz, nz, fma2(dy, ny, mul2(dx, nx)));
+    f2_t J[6];
+    J[0] = fma2(nz, py, neg2(mul2(ny, pz)));
+    J[1] = fma2(nx, pz, neg2(mul2(nz, px)));
+    J[2] = fma2(ny, px, neg2(mul2(nx, py)));
+    J[3] = nx; J[4] = ny; J[5] = nz;
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = i; j < 6; j++) { a.s[k] = fma2(J[i], J[j], a.s[k]); k++; }
+#pragma unroll
+    for (int i = 0; i < 6; i++) a.s[21 + i] = fma2(J[i], r, a.s[21 + i]);
+    a.s[27] = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, a.s[27])));
 }
 
 struct Acc1 { float v[32]; };     // scalar accumulation: one FFMA per sum (first generation)
@@ -362,6 +417,10 @@ __device__ __forceinline__ void acc_unpack(const Acc1& a, float (&v)[32]) {
 __device__ __forceinline__ void acc_unpack(const Acc2& a, float (&v)[32]) { unpack_acc2(a, v); }
 #ifndef PR_FFMA2
 #define PR_FFMA2 1
+#endif
+// PR_PAIR: the two-points-per-instruction path (AccP) for the packed projective scene in the persistent driver
+#ifndef PR_PAIR
+#define PR_PAIR 1
 #endif
 #if PR_FFMA2
 typedef Acc2 AccT;
@@ -404,7 +463,11 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 }
 __device__ __forceinline__ unsigned atom_add_release(unsigned* p, unsigned v) {
     unsigned old;
+#ifdef PR_DBG_NOFENCE       // what-if: no release fence in front of the ticket (incorrect ordering, timing only)
+    asm volatile("atom.add.relaxed.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+#else
     asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+#endif
     return old;
 }
 
@@ -436,13 +499,10 @@ __device__ __noinline__ void finish_pass_impl(HypState* st, const float* S, unsi
     for (int i = 0; i < 12; i++) T[i] = RELEASE ? __ldcg(&st->T[i]) : st->T[i];
     T[12] = 0.f; T[13] = 0.f; T[14] = 0.f; T[15] = 1.f;
     if (!ret) {
-        float A[36], b[6], E[16];
+        float Sr[29], E[16];
 #pragma unroll
-        for (int i = 0; i < 6; i++) b[i] = S[21 + i];
-        int shift = 0;
-        for (int y = 0; y < 6; y++)
-            for (int x = y; x < 6; x++) { A[x + y * 6] = S[shift]; A[y + x * 6] = S[shift]; shift++; }   // icp.cu:198-205
-        solve_666(A, b, E);                                    // icp.cu:207
+        for (int i = 0; i < 29; i++) Sr[i] = S[i];
+        solve_666_unrolled(Sr, E);                             // unpack icp.cu:198-205 + solve icp.cu:207
         // result.transformation_ = extrinsic * result.transformation_ (icp.cu:212); geometry.h:107-111
         // sums each dot product from index 3 down to 0.
         float Tn[12];
@@ -654,23 +714,22 @@ struct IcpCtl {            // device-side control block
     unsigned pad[30];
 };
 
-// packed projective scene: two aligned arrays, per pixel {qx,qy,qz,nx} (16 B) and {ny,nz} (8 B)
+// packed projective scene: one 32-byte record per pixel (= one L2 sector per correspondence).  Two separate
+// arrays ({qx,qy,qz,nx} 16 B + {ny,nz} 8 B) cost 3x the time: measured 2.08 ms vs 0.71 ms with the second gather removed.
 struct PackedScene {
     int W, H;
     float fW, fH;
     float max_dist;
     float fx, fy, cx05, cy05;     // cx + 0.5, cy + 0.5
-    const float4* qn;
-    const float2* n2;
+    const float4* rec;            // pixel i: rec[2i] = {qx,qy,qz,nx}, rec[2i+1] = {ny,nz,0,0}
 };
 
 __global__ void __launch_bounds__(256)
-scene_pack_kernel(const float* __restrict__ pcd, const float* __restrict__ nrm, size_t n_px, float4* __restrict__ qn,
-                  float2* __restrict__ n2) {
+scene_pack_kernel(const float* __restrict__ pcd, const float* __restrict__ nrm, size_t n_px, float4* __restrict__ rec) {
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n_px) return;
-    qn[i] = make_float4(pcd[3 * i], pcd[3 * i + 1], pcd[3 * i + 2], nrm[3 * i]);
-    n2[i] = make_float2(nrm[3 * i + 1], nrm[3 * i + 2]);
+    rec[2 * i] = make_float4(pcd[3 * i], pcd[3 * i + 1], pcd[3 * i + 2], nrm[3 * i]);
+    rec[2 * i + 1] = make_float4(nrm[3 * i + 1], nrm[3 * i + 2], 0.f, 0.f);
 }
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -710,6 +769,21 @@ __device__ __forceinline__ void sts32(unsigned addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
+// one scene record: PR_REC 2 = a single 256-bit load (LDG.E.256, sm_100), 1 = two 128-bit loads of the same sector
+#ifndef PR_REC
+#define PR_REC 2
+#endif
+__device__ __forceinline__ void load_rec(const PackedScene& s, int idx, float4& A, float2& B) {
+    const float4* r = s.rec + 2 * (size_t)(unsigned)idx;
+#if PR_REC == 2
+    float u0, u1;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(A.x), "=f"(A.y), "=f"(A.z), "=f"(A.w), "=f"(B.x), "=f"(B.y), "=f"(u0), "=f"(u1) : "l"(r));
+#else
+    A = __ldg(r);
+    B = __ldg(reinterpret_cast<const float2*>(r + 1));
+#endif
+}
 __device__ __forceinline__ void transform(const float* T, float x, float y, float z, float& px, float& py, float& pz) {
     // transform_pcd_cuda (icp.cu:147-149) with the accumulated transform
     px = fmaf(T[2], z, fmaf(T[1], y, fmaf(T[0], x, T[3])));
@@ -757,8 +831,7 @@ __device__ __forceinline__ void group_projective(const PackedScene& s, unsigned 
 #pragma unroll
     for (int k = 0; k < kIlp; k++) {
         if (ok[k]) {
-            A[k] = __ldg(s.qn + idx[k]);
-            B[k] = __ldg(s.n2 + idx[k]);
+            load_rec(s, idx[k], A[k], B[k]);
         }
     }
 #pragma unroll
@@ -773,6 +846,7 @@ __device__ __forceinline__ void group_projective(const PackedScene& s, unsigned 
     }
 }
 
+
 // one warp tile (n <= kWTile points at shared address `tile`), packed projective scene
 __device__ __forceinline__ void compute_tile(const PackedScene& s, unsigned tile, unsigned n, const float* T, AccT& acc) {
     const unsigned lane = threadIdx.x & 31;
@@ -785,6 +859,143 @@ __device__ __forceinline__ void compute_tile(const PackedScene& s, unsigned tile
     for (; first < n_full; first += kGroup, addr += 12 * kGroup) group_projective<false>(s, addr, first, n, T, acc);
     if (n_full < n) group_projective<true>(s, addr, first, n, T, acc);
 }
+
+
+#if PR_PAIR
+// 1/z with the sign folded in: returns -(1/z) refined by one Newton step.  Bit for bit the negation of
+// fast_rcp(z) (rcp.approx is odd, (-z)*r == z*(-r), and round-to-nearest is symmetric).
+__device__ __forceinline__ f2_t fast_nrcp2(f2_t z) {
+    float z0, z1, r0, r1;
+    unpk2(z, z0, z1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(-z0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(-z1));
+    const f2_t nr = pk2(r0, r1);
+    const f2_t e = fma2(z, nr, bc2(1.0f));
+    return fma2(nr, e, nr);
+}
+// group_projective with two points per instruction (see AccP).  Lane l owns points l + 32k of the group;
+// points 2j and 2j+1 form pair j.  No branches: a rejected point is turned into q = p, n = 0 by the
+// selects that also move the gathered values into the pair registers.  A non-finite transformed point
+// would turn into NaN sums here (0 * inf); the item loop detects that and redoes the item with the
+// per-point path (slow_item), so such clouds stay correct and everything else pays nothing for them.
+template <bool TAIL>
+__device__ __forceinline__ void group_projective(const PackedScene& s, unsigned addr, unsigned first, unsigned n,
+                                                 const float* T, AccP& acc) {
+    constexpr int NP = kIlp / 2;
+    static_assert(kIlp % 2 == 0, "pairs");
+    f2_t px[NP], py[NP], pz[NP];
+    int idx[kIlp];
+    bool ok[kIlp];
+    const float nfx = -s.fx, nfy = -s.fy;
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+        float x0 = lds32(addr + 384 * (2 * j)), y0 = lds32(addr + 384 * (2 * j) + 4), z0 = lds32(addr + 384 * (2 * j) + 8);
+        float x1 = lds32(addr + 384 * (2 * j + 1)), y1 = lds32(addr + 384 * (2 * j + 1) + 4), z1 = lds32(addr + 384 * (2 * j + 1) + 8);
+        bool in0 = true, in1 = true;
+        if (TAIL) {     // the tile holds stale data past the end of the item
+            in0 = first + 32 * (2 * j) < n; in1 = first + 32 * (2 * j + 1) < n;
+            x0 = in0 ? x0 : 0.f; y0 = in0 ? y0 : 0.f; z0 = in0 ? z0 : 0.f;
+            x1 = in1 ? x1 : 0.f; y1 = in1 ? y1 : 0.f; z1 = in1 ? z1 : 0.f;
+        }
+        const f2_t x = pk2(x0, x1), y = pk2(y0, y1), z = pk2(z0, z1);
+        // transform_pcd_cuda (icp.cu:147-149) with the accumulated transform, same FMA chain as transform()
+        px[j] = fma2(bc2(T[2]), z, fma2(bc2(T[1]), y, fma2(bc2(T[0]), x, bc2(T[3]))));
+        py[j] = fma2(bc2(T[6]), z, fma2(bc2(T[5]), y, fma2(bc2(T[4]), x, bc2(T[7]))));
+        pz[j] = fma2(bc2(T[10]), z, fma2(bc2(T[9]), y, fma2(bc2(T[8]), x, bc2(T[11]))));
+        const f2_t nrz = fast_nrcp2(pz[j]);
+        // fma(px*rz, fx, cx+0.5) == fma(px*(-rz), -fx, cx+0.5)
+        float uf0, uf1, vf0, vf1;
+        unpk2(fma2(bc2(nfx), mul2(px[j], nrz), bc2(s.cx05)), uf0, uf1);
+        unpk2(fma2(bc2(nfy), mul2(py[j], nrz), bc2(s.cy05)), vf0, vf1);
+        const int u0 = __float2int_rz(fmaxf(uf0, -2.0f)), v0 = __float2int_rz(fmaxf(vf0, -2.0f));
+        const int u1 = __float2int_rz(fmaxf(uf1, -2.0f)), v1 = __float2int_rz(fmaxf(vf1, -2.0f));
+        ok[2 * j] = ((unsigned)u0 < (unsigned)s.W) & ((unsigned)v0 < (unsigned)s.H) & in0;
+        ok[2 * j + 1] = ((unsigned)u1 < (unsigned)s.W) & ((unsigned)v1 < (unsigned)s.H) & in1;
+        idx[2 * j] = v0 * s.W + u0;
+        idx[2 * j + 1] = v1 * s.W + u1;
+#ifdef PR_DBG_NOGATHER      // what-if: every gather hits the same few L1 lines (wrong results, timing only)
+        idx[2 * j] = (threadIdx.x & 31) + 32 * (2 * j); idx[2 * j + 1] = (threadIdx.x & 31) + 32 * (2 * j + 1);
+#endif
+#ifdef PR_DBG_WRAP          // what-if (use with PR_DBG_NOACC so that every pass runs): same access pattern folded
+                            // into a PR_DBG_WRAP-pixel window in the middle of the object
+        idx[2 * j] = 280 * 640 + 300 + (idx[2 * j] & (PR_DBG_WRAP - 1)); idx[2 * j + 1] = 280 * 640 + 300 + (idx[2 * j + 1] & (PR_DBG_WRAP - 1));
+#endif
+    }
+    float4 A[kIlp];
+    float2 B[kIlp];
+#pragma unroll
+    for (int k = 0; k < kIlp; k++) {
+        if (ok[k]) {
+#ifdef PR_DBG_NOLOAD        // what-if (with PR_DBG_NOACC): no scene access at all, every in-image point "valid"
+            A[k] = make_float4(1.f, 2.f, 0.3f, 0.5f); B[k] = make_float2(0.5f, 0.7f);
+#else
+            load_rec(s, idx[k], A[k], B[k]);
+#endif
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+        const float4 A0 = A[2 * j], A1 = A[2 * j + 1];
+        const float2 B0 = B[2 * j], B1 = B[2 * j + 1];
+        float px0, px1, py0, py1, pz0, pz1;
+        unpk2(px[j], px0, px1); unpk2(py[j], py0, py1); unpk2(pz[j], pz0, pz1);
+        const bool v0 = ok[2 * j] && A0.z > 0.f && fabsf(pz0 - A0.z) <= s.max_dist;          // depth_scene.h:42
+        const bool v1 = ok[2 * j + 1] && A1.z > 0.f && fabsf(pz1 - A1.z) <= s.max_dist;
+        const f2_t qx = pk2(v0 ? A0.x : px0, v1 ? A1.x : px1);
+        const f2_t qy = pk2(v0 ? A0.y : py0, v1 ? A1.y : py1);
+        const f2_t qz = pk2(v0 ? A0.z : pz0, v1 ? A1.z : pz1);
+        const f2_t nx = pk2(v0 ? A0.w : 0.f, v1 ? A1.w : 0.f);
+        const f2_t ny = pk2(v0 ? B0.x : 0.f, v1 ? B1.x : 0.f);
+        const f2_t nz = pk2(v0 ? B0.y : 0.f, v1 ? B1.y : 0.f);
+#ifdef PR_DBG_NOACC         // what-if: no Jacobian / sums (wrong results, timing only)
+        acc.s[0] = fma2(qx, nx, acc.s[0]); acc.s[1] = fma2(qy, ny, acc.s[1]); acc.s[2] = fma2(qz, nz, acc.s[2]);
+#else
+        accumulate_pair(acc, px[j], py[j], pz[j], qx, qy, qz, nx, ny, nz);
+#endif
+        if (v0) acc.cnt_a += 1.0f;
+        if (v1) acc.cnt_b += 1.0f;
+    }
+}
+
+__device__ __forceinline__ void compute_tile(const PackedScene& s, unsigned tile, unsigned n, const float* T, AccP& acc) {
+    const unsigned lane = threadIdx.x & 31;
+    unsigned addr = tile + 12 * lane;
+    unsigned first = lane;
+    constexpr unsigned kGroup = 32 * kIlp;
+    static_assert(kWTile % kGroup == 0, "a tail group must not read past the tile");
+    const unsigned n_full = n - n % kGroup;
+#pragma unroll 1
+    for (; first < n_full; first += kGroup, addr += 12 * kGroup) group_projective<false>(s, addr, first, n, T, acc);
+    if (n_full < n) group_projective<true>(s, addr, first, n, T, acc);
+}
+
+// per-point query against the packed scene with the pixel selection of group_projective (robust path)
+__device__ __forceinline__ bool query(const PackedScene& s, float px, float py, float pz, Corr& c) {
+    const float rz = fast_rcp(pz);
+    const int ui = __float2int_rz(fmaxf(fmaf(px * rz, s.fx, s.cx05), -2.0f));
+    const int vi = __float2int_rz(fmaxf(fmaf(py * rz, s.fy, s.cy05), -2.0f));
+    if (!(((unsigned)ui < (unsigned)s.W) & ((unsigned)vi < (unsigned)s.H))) return false;
+    float4 A; float2 B;
+    load_rec(s, vi * s.W + ui, A, B);
+    if (!(A.z > 0.f && fabsf(pz - A.z) <= s.max_dist)) return false;
+    c.qx = A.x; c.qy = A.y; c.qz = A.z; c.nx = A.w; c.ny = B.x; c.nz = B.y;
+    return true;
+}
+// the whole item again, point by point from global memory (taken only when the packed path produced NaN sums)
+__device__ __noinline__ float slow_item(const PackedScene& s, const float* __restrict__ g, unsigned n, const float* T) {
+    const unsigned lane = threadIdx.x & 31;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = 0.f;
+    for (unsigned i = lane; i < n; i += 32) {
+        float px, py, pz;
+        transform(T, g[3 * i], g[3 * i + 1], g[3 * i + 2], px, py, pz);
+        Corr c;
+        if (query(s, px, py, pz, c)) accumulate(v, px, py, pz, c);
+    }
+    return warp_transpose_reduce(v);
+}
+#endif
 
 // one warp tile, any scene with a per-point query() (nearest neighbour)
 template <class SceneT>
@@ -806,7 +1017,15 @@ __device__ __noinline__ void warp_finish_hypothesis(HypState* st, const float* p
     const unsigned lane = threadIdx.x & 31;
     float sum = 0.f;
     const unsigned cb = __ldcg(&st->chunk_begin), nc = __ldcg(&st->n_chunks);
-    for (unsigned j = 0; j < nc; j++) sum += __ldcg(partials + (size_t)(cb + j) * kPartialStride + lane);
+    // chunk order (deterministic); four loads in flight per step
+    unsigned j = 0;
+    const float* pp = partials + (size_t)cb * kPartialStride + lane;
+    for (; j + 4 <= nc; j += 4) {
+        const float a0 = __ldcg(pp + (size_t)j * kPartialStride), a1 = __ldcg(pp + (size_t)(j + 1) * kPartialStride);
+        const float a2 = __ldcg(pp + (size_t)(j + 2) * kPartialStride), a3 = __ldcg(pp + (size_t)(j + 3) * kPartialStride);
+        sum = (((sum + a0) + a1) + a2) + a3;
+    }
+    for (; j < nc; j++) sum += __ldcg(pp + (size_t)j * kPartialStride);
     float S[29];
 #pragma unroll
     for (int i = 0; i < 29; i++) S[i] = __shfl_sync(0xffffffffu, sum, i);
@@ -842,6 +1061,11 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
                       HypState* state, float* partials, SceneT scene, pr_icp_criteria crit,
                       pr_registration_result* results) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+#if PR_PAIR
+    using AccK = typename std::conditional<std::is_same<SceneT, PackedScene>::value, AccP, AccT>::type;
+#else
+    using AccK = AccT;
+#endif
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned tile0 = smem_u32(smem_raw) + warp * (kWStages * kWTileBytes);
     const unsigned bar0 = smem_u32(smem_raw) + kPWarps * kWStages * kWTileBytes + warp * (kWStages * 8);
@@ -897,15 +1121,17 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
         }
         const bool skip = __shfl_sync(0xffffffffu, flag, 0) != 0;
         float T[12];
-        AccT acc;
+        AccK acc;
 #pragma unroll
         for (int i = 0; i < 12; i++) T[i] = skip ? 0.f : __ldcg(&st->T[i]);
         acc_zero(acc);
 
-        for (unsigned t = 0; t < n_tiles; t++) {
-            // ---- prefetch: next tile of this item, or the first tile of the next claimed item
-            bool tma_next = false;
+        // tile bookkeeping shared by both loop shapes: on entering tile t, prefetch its successor (next
+        // tile of this item, or the first tile of the next claimed item) and wait for tile t itself
+        bool tma_next = false;
+        auto enter_tile = [&](unsigned t) {
             const unsigned other = stage ^ 1;
+            tma_next = false;
             if (t + 1 < n_tiles) {
                 tma_next = stage_tile(g + (size_t)(t + 1) * kWTileFloats, min((unsigned)kWTile, n_pts - (t + 1) * kWTile), pts_end,
                                       tile0 + other * kWTileBytes, bar0 + 8 * other);
@@ -918,22 +1144,35 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
                     tma_next = stage_tile(pts + 3 * (size_t)next_info.y, min((unsigned)kWTile, next_info.z), pts_end,
                                           tile0 + other * kWTileBytes, bar0 + 8 * other);
             }
-            // ---- consume tile t
             if (tma_cur) {
                 mbar_wait(bar0 + 8 * stage, (parity >> stage) & 1u);
                 parity ^= (1u << stage);
             }
-            if (!skip) compute_tile(scene, tile0 + stage * kWTileBytes, min((unsigned)kWTile, n_pts - t * kWTile), T, acc);
-            __syncwarp();            // every lane is done with this stage before it is refilled
-            stage = other;
+        };
+        auto leave_tile = [&]() {
+            __syncwarp();            // every lane is done reading this stage before it is refilled
+            stage ^= 1;
             tma_cur = tma_next;
+        };
+        // (tried: issuing the gathers of group g+1 before consuming group g from a second register set.  It
+        // does not overlap anything: ptxas tracks both sets on the same scoreboard, so the first consume
+        // waits for the newest gathers as well -- measured 2.19 -> 2.39..2.54 ms.)
+        for (unsigned t = 0; t < n_tiles; t++) {
+            enter_tile(t);
+            if (!skip) compute_tile(scene, tile0 + stage * kWTileBytes, min((unsigned)kWTile, n_pts - t * kWTile), T, acc);
+            leave_tile();
         }
 
         // ---- item complete: reduce over the warp, deposit, maybe finish the pass of this hypothesis
         if (!skip) {
             float v[32];
             acc_unpack(acc, v);
-            const float mine = warp_transpose_reduce(v);       // lane l = sum of value l
+            float mine = warp_transpose_reduce(v);             // lane l = sum of value l
+#if PR_PAIR
+            if constexpr (std::is_same<SceneT, PackedScene>::value) {
+                if (__any_sync(0xffffffffu, mine != mine)) mine = slow_item(scene, g, n_pts, T);
+            }
+#endif
             __stcg(partials + (size_t)c * kPartialStride + lane, mine);
             __syncwarp();            // all 32 partial stores precede lane 0's release below
             int is_last = 0;
@@ -974,7 +1213,7 @@ icp_apply_kernel(float* __restrict__ pts, const uint32_t* __restrict__ offsets, 
 inline size_t icp_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct IcpWs {
-    HypState* state; uint32_t* chunk_hyp; uint4* chunk_info; IcpCtl* ctl; float* partials; float4* packed; float2* packed2;
+    HypState* state; uint32_t* chunk_hyp; uint4* chunk_info; IcpCtl* ctl; float* partials; float4* packed;
     size_t max_chunks, bytes;
 };
 
@@ -998,8 +1237,7 @@ inline IcpWs carve_icp_ws(void* base, size_t n_hyp, size_t capacity_points, size
     ws.chunk_info = (uint4*)take(ws.max_chunks * 16);
     ws.ctl = (IcpCtl*)take(sizeof(IcpCtl));
     ws.partials = (float*)take(ws.max_chunks * kPartialStride * 4);
-    ws.packed = (float4*)take(scene_pixels * 16);
-    ws.packed2 = (float2*)take(scene_pixels * 8);
+    ws.packed = (float4*)take(scene_pixels * 32);
     ws.bytes = used;
     return ws;
 }
@@ -1058,7 +1296,9 @@ int run_icp(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_
     int rc = persistent_grid<PScene>(&grid);
     if (rc != PR_OK) return rc;
     grid = (int)std::min<size_t>((size_t)grid, (max_items + kPWarps - 1) / kPWarps);
-    icp_persistent_kernel<PScene><<<grid, kPThreads, kPersistSmem, stream>>>(
+    int threads = kPThreads;
+    if (const char* e = getenv("PR_ICP_WARPS")) threads = std::max(1, std::min(kPWarps, atoi(e))) * 32;   // experiments
+    icp_persistent_kernel<PScene><<<grid, threads, kPersistSmem, stream>>>(
         pts_dev, capacity_points, ws.chunk_info, ws.ctl, ws.state, ws.partials, pscene, crit, results_dev);
     count_launch(2);
     if (flags & PR_ICP_UPDATE_POINTS) {
@@ -1149,9 +1389,9 @@ int pr_icp_projective_batch(float* pts_dev, const uint32_t* offsets_dev, const u
     cudaStream_t stream = as_stream(stream_);
     PackedScene ps;
     ps.W = s.W; ps.H = s.H; ps.fW = s.fW; ps.fH = s.fH; ps.max_dist = s.max_dist;
-    ps.fx = s.fx; ps.fy = s.fy; ps.cx05 = s.cx + 0.5f; ps.cy05 = s.cy + 0.5f; ps.qn = ws.packed; ps.n2 = ws.packed2;
+    ps.fx = s.fx; ps.fy = s.fy; ps.cx05 = s.cx + 0.5f; ps.cy05 = s.cy + 0.5f; ps.rec = ws.packed;
     if (!use_pass_driver()) {
-        scene_pack_kernel<<<(unsigned)((n_px + 255) / 256), 256, 0, stream>>>(s.pcd, s.nrm, n_px, ws.packed, ws.packed2);
+        scene_pack_kernel<<<(unsigned)((n_px + 255) / 256), 256, 0, stream>>>(s.pcd, s.nrm, n_px, ws.packed);
         count_launch();
     }
     return run_icp(pts_dev, offsets_dev, counts_dev, n_hyp, capacity_points, s, ps, criteria, results_dev, flags, ws, stream);
@@ -1198,7 +1438,16 @@ int pr_icp_nn_batch(float* pts_dev, const uint32_t* offsets_dev, const uint32_t*
 
 int pr_solve_666(const float A[36], const float b[6], float T[16]) {
     if (!A || !b || !T) return PR_ERR_INVALID_ARGUMENT;
-    solve_666(A, b, T);
+    // the register-resident form the device runs (same arithmetic as solve_666): pack the lower triangle
+    // the way thrust__pcd2Ab orders it (icp.h:165-197)
+    float S[29], E[16];
+    int shift = 0;
+    for (int y = 0; y < 6; y++)
+        for (int x = y; x < 6; x++) S[shift++] = A[x + 6 * y];
+    for (int i = 0; i < 6; i++) S[21 + i] = b[i];
+    S[27] = 0.f; S[28] = 0.f;
+    solve_666_unrolled(S, E);
+    for (int i = 0; i < 16; i++) T[i] = E[i];
     return PR_OK;
 }
 

@@ -19,6 +19,29 @@ namespace prb {
 
 template <class T> __host__ __device__ __forceinline__ void swap_vals(T& a, T& b) { T t = a; a = b; b = t; }
 
+// x = (rx, ry, rz, tx, ty, tz) -> row-major 4x4 (TransformVector6dToMatrix4d, icp.cpp:7-17)
+__host__ __device__ __forceinline__ void pose_from_x(const double* x, float* E) {
+    // q = qz * qy * qx with q_axis(angle) = (cos(angle/2), sin(angle/2) * axis)
+    const double cz = cos(0.5 * x[2]), sz = sin(0.5 * x[2]);
+    const double cy = cos(0.5 * x[1]), sy = sin(0.5 * x[1]);
+    const double cx = cos(0.5 * x[0]), sx = sin(0.5 * x[0]);
+    // qz*qy (Hamilton product with the structural zeros kept as exact 0 terms dropped)
+    const double aw = cz * cy, ax = -(sz * sy), ay = cz * sy, az = sz * cy;
+    // (qz*qy) * qx, qx = (cx, sx, 0, 0)
+    const double qw = aw * cx - ax * sx;
+    const double qx = aw * sx + ax * cx;
+    const double qy = ay * cx + az * sx;
+    const double qz = az * cx - ay * sx;
+    const double tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
+    const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
+    const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
+    const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+    E[0] = (float)(1.0 - (tyy + tzz)); E[1] = (float)(txy - twz); E[2] = (float)(txz + twy); E[3] = (float)x[3];
+    E[4] = (float)(txy + twz); E[5] = (float)(1.0 - (txx + tzz)); E[6] = (float)(tyz - twx); E[7] = (float)x[4];
+    E[8] = (float)(txz - twy); E[9] = (float)(tyz + twx); E[10] = (float)(1.0 - (txx + tyy)); E[11] = (float)x[5];
+    E[12] = 0.f; E[13] = 0.f; E[14] = 0.f; E[15] = 1.f;
+}
+
 // A: 6x6 symmetric (any of row/column-major), b: 6.  E: row-major 4x4 (16 floats).
 __host__ __device__ inline void solve_666(const float* A, const float* b, float* E) {
     const int n = 6;
@@ -59,25 +82,97 @@ __host__ __device__ inline void solve_666(const float* A, const float* b, float*
     for (int i = n - 1; i >= 0; i--) for (int j = i + 1; j < n; j++) x[i] -= a[j][i] * x[j];
     for (int k = n - 1; k >= 0; k--) if (tr[k] != k) swap_vals(x[k], x[tr[k]]);
 
-    // q = qz * qy * qx with q_axis(angle) = (cos(angle/2), sin(angle/2) * axis)
-    const double cz = cos(0.5 * x[2]), sz = sin(0.5 * x[2]);
-    const double cy = cos(0.5 * x[1]), sy = sin(0.5 * x[1]);
-    const double cx = cos(0.5 * x[0]), sx = sin(0.5 * x[0]);
-    // qz*qy (Hamilton product with the structural zeros kept as exact 0 terms dropped)
-    const double aw = cz * cy, ax = -(sz * sy), ay = cz * sy, az = sz * cy;
-    // (qz*qy) * qx, qx = (cx, sx, 0, 0)
-    const double qw = aw * cx - ax * sx;
-    const double qx = aw * sx + ax * cx;
-    const double qy = ay * cx + az * sx;
-    const double qz = az * cx - ay * sx;
-    const double tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
-    const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
-    const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
-    const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
-    E[0] = (float)(1.0 - (tyy + tzz)); E[1] = (float)(txy - twz); E[2] = (float)(txz + twy); E[3] = (float)x[3];
-    E[4] = (float)(txy + twz); E[5] = (float)(1.0 - (txx + tzz)); E[6] = (float)(tyz - twx); E[7] = (float)x[4];
-    E[8] = (float)(txz - twy); E[9] = (float)(tyz + twx); E[10] = (float)(1.0 - (txx + tyy)); E[11] = (float)x[5];
-    E[12] = 0.f; E[13] = 0.f; E[14] = 0.f; E[15] = 1.f;
+    pose_from_x(x, E);
+}
+
+// Same arithmetic as solve_666, operation for operation, with every array index a compile-time constant:
+// the data-dependent pivot is applied as "if (piv == p) swap(...)" over the unrolled candidates, so the
+// whole 6x6 factorisation lives in registers.  (solve_666's a[piv][j] indexing puts the matrix in local
+// memory: measured ~21 us per solve on one B200 thread, 13 % of the ICP kernel's warp time.)
+template <int K> struct PivotStep {
+    __host__ __device__ static __forceinline__ void run(double (&a)[6][6], int (&tr)[6]) {
+        int piv = K;
+        double big = fabs(a[K][K]);
+#pragma unroll
+        for (int i = K + 1; i < 6; i++) if (fabs(a[i][i]) > big) { big = fabs(a[i][i]); piv = i; }
+        tr[K] = piv;
+#pragma unroll
+        for (int p = K + 1; p < 6; p++) {
+            if (piv == p) {
+#pragma unroll
+                for (int j = 0; j < K; j++) swap_vals(a[K][j], a[p][j]);
+#pragma unroll
+                for (int i = p + 1; i < 6; i++) swap_vals(a[i][K], a[i][p]);
+                swap_vals(a[K][K], a[p][p]);
+#pragma unroll
+                for (int i = K + 1; i < p; i++) swap_vals(a[i][K], a[p][i]);
+            }
+        }
+        if (K > 0) {
+            double tmp[6];
+#pragma unroll
+            for (int j = 0; j < K; j++) tmp[j] = a[j][j] * a[K][j];
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < K; j++) acc += a[K][j] * tmp[j];
+            a[K][K] -= acc;
+#pragma unroll
+            for (int i = K + 1; i < 6; i++) {
+                double acc2 = 0.0;
+#pragma unroll
+                for (int j = 0; j < K; j++) acc2 += a[i][j] * tmp[j];
+                a[i][K] -= acc2;
+            }
+        }
+        if (K + 1 < 6 && fabs(a[K][K]) > 0.0) {
+#pragma unroll
+            for (int i = K + 1; i < 6; i++) a[i][K] /= a[K][K];
+        }
+    }
+};
+
+// S: the 29 sums in thrust__pcd2Ab's order (icp.h:165-206); unpacked as icp.cu:198-205 does.
+__host__ __device__ __forceinline__ void solve_666_unrolled(const float (&S)[29], float (&E)[16]) {
+    double a[6][6], x[6];
+    int tr[6];
+    {
+        int shift = 0;
+#pragma unroll
+        for (int y = 0; y < 6; y++)
+#pragma unroll
+            for (int xx = y; xx < 6; xx++) {
+                const double v = (double)S[shift++];
+                a[xx][y] = v + (xx == y ? 0.01 : 0.0);
+                a[y][xx] = a[xx][y];
+            }
+#pragma unroll
+        for (int i = 0; i < 6; i++) x[i] = (double)S[21 + i];
+    }
+    PivotStep<0>::run(a, tr); PivotStep<1>::run(a, tr); PivotStep<2>::run(a, tr);
+    PivotStep<3>::run(a, tr); PivotStep<4>::run(a, tr); PivotStep<5>::run(a, tr);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+#pragma unroll
+        for (int p = k + 1; p < 6; p++) if (tr[k] == p) swap_vals(x[k], x[p]);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+#pragma unroll
+        for (int j = 0; j < i; j++) x[i] -= a[i][j] * x[j];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) { if (fabs(a[i][i]) > DBL_MIN) x[i] /= a[i][i]; else x[i] = 0.0; }
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+#pragma unroll
+        for (int j = i + 1; j < 6; j++) x[i] -= a[j][i] * x[j];
+    }
+#pragma unroll
+    for (int k = 5; k >= 0; k--) {
+#pragma unroll
+        for (int p = k + 1; p < 6; p++) if (tr[k] == p) swap_vals(x[k], x[p]);
+    }
+    pose_from_x(x, E);
 }
 
 }  // namespace prb

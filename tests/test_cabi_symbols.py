@@ -60,6 +60,14 @@ def test_host_entry_points_match_oracle(port, golden, tmp_path):
         A = (J.T @ J).astype(np.float32); A = ((A + A.T) / 2).astype(np.float32)
         b = rng.normal(size=6).astype(np.float32)
         assert np.allclose(api.eigen_solver_666(A, b), port.solve_666(A, b), rtol=0, atol=2e-7)
+    # the entry point runs the register-resident (fully unrolled, predicated-pivot) form the device uses; on the
+    # host it must agree with the oracle's loop form bit for bit, also when every pivot step swaps
+    for _ in range(200):
+        d = np.sort(rng.uniform(0.5, 50.0, size=6)).astype(np.float32)        # ascending diagonal: pivots at every step
+        Q = rng.normal(scale=0.05, size=(6, 6)).astype(np.float32)
+        A = (np.diag(d) + Q + Q.T).astype(np.float32)
+        b = rng.normal(size=6).astype(np.float32)
+        assert np.array_equal(api.eigen_solver_666(A, b), port.solve_666(A, b))
 
 
 def _write_ply(path, verts, faces, binary):
