@@ -681,10 +681,10 @@ icp_pass_kernel(const float* __restrict__ pts, const uint32_t* __restrict__ offs
 // CTA-wide barrier anywhere; the only cross-warp synchronisation is the per-hypothesis
 // acquire/release on HypState::pass / done and the ticket counter.
 #ifndef PR_WTILE
-#define PR_WTILE 512
+#define PR_WTILE 1024
 #endif
 #ifndef PR_CHUNK
-#define PR_CHUNK 2048
+#define PR_CHUNK 4096
 #endif
 // Tuning (measured on B200, 512 hypotheses x 31 passes, ICP only): ILP 4 / 2 CTAs per SM 2.83 ms;
 // ILP 8 / 1 CTA of 256 threads 2.29 ms; ILP 8 / 384 threads 2.68 ms; tile 256 2.62 ms.  Eight gathers in
@@ -700,13 +700,14 @@ icp_pass_kernel(const float* __restrict__ pts, const uint32_t* __restrict__ offs
 #endif
 constexpr int kPThreads = PR_PTHREADS;         // threads per CTA of the persistent kernel
 constexpr int kPWarps = kPThreads / 32;
-constexpr int kWTile = PR_WTILE;               // points per warp tile (6 KB at 512)
-constexpr int kWTileFloats = kWTile * 3;
-constexpr int kWTileBytes = kWTileFloats * 4;
+constexpr int kWTile = PR_WTILE;               // points per warp tile of the projective driver (12 KB at 1024)
+constexpr int kWTileNn = 512;                  // nearest-neighbour scenes: small tiles, so that several CTAs fit an SM
 constexpr int kWStages = 2;
-constexpr uint32_t kPersistChunk = PR_CHUNK;   // points per work item
+constexpr uint32_t kPersistChunk = PR_CHUNK;   // points per work item of a large batch (see persist_chunk_points)
 constexpr int kIlp = PR_ILP;                   // points per lane per group (gathers in flight per lane)
-constexpr int kPersistSmem = kPWarps * kWStages * kWTileBytes + kPWarps * kWStages * 8;
+struct PackedScene;
+template <class SceneT> struct TileOf { static constexpr int kPoints = std::is_same<SceneT, PackedScene>::value ? kWTile : kWTileNn; };
+template <class SceneT> constexpr int persist_smem() { return kPWarps * kWStages * (TileOf<SceneT>::kPoints * 12) + kPWarps * kWStages * 8; }
 
 struct IcpCtl {            // device-side control block
     unsigned next_item;    // work-item claim counter
@@ -1055,8 +1056,10 @@ __device__ __forceinline__ bool stage_tile(const float* src, unsigned n, uintptr
     return tma;
 }
 
+// projective: one CTA of register-rich warps per SM; nearest neighbour: two CTAs (the tree walk hides latency with warps)
+template <class SceneT> struct MinBlocksOf { static constexpr int kValue = std::is_same<SceneT, PackedScene>::value ? PR_MINB : 2; };
 template <class SceneT>
-__global__ void __launch_bounds__(kPThreads, PR_MINB)
+__global__ void __launch_bounds__(kPThreads, MinBlocksOf<SceneT>::kValue)
 icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, const uint4* __restrict__ chunk_info, IcpCtl* ctl,
                       HypState* state, float* partials, SceneT scene, pr_icp_criteria crit,
                       pr_registration_result* results) {
@@ -1066,6 +1069,9 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
 #else
     using AccK = AccT;
 #endif
+    constexpr int kWTile = TileOf<SceneT>::kPoints;     // shadows the projective constant on purpose
+    constexpr int kWTileFloats = kWTile * 3;
+    constexpr int kWTileBytes = kWTileFloats * 4;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned tile0 = smem_u32(smem_raw) + warp * (kWStages * kWTileBytes);
     const unsigned bar0 = smem_u32(smem_raw) + kPWarps * kWStages * kWTileBytes + warp * (kWStages * 8);
@@ -1098,6 +1104,14 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
     bool tma_cur = false;               // was the next tile to consume fetched by TMA?
     if (item < n_items)
         tma_cur = stage_tile(pts + 3 * (size_t)info.y, min((unsigned)kWTile, info.z), pts_end, tile0 + stage * kWTileBytes, bar0 + 8 * stage);
+    // arrival ticket of a deposited partial; the warp that takes the last ticket of a hypothesis finishes its pass
+    auto take_ticket = [&](HypState* tst, unsigned n_h, unsigned th) {
+        __syncwarp();            // all 32 partial stores precede lane 0's release below
+        int is_last = 0;
+        if (lane == 0) is_last = (atom_add_release(&tst->arrived, 1u) == __ldcg(&tst->n_chunks) - 1) ? 1 : 0;
+        is_last = __shfl_sync(0xffffffffu, is_last, 0);
+        if (is_last) warp_finish_hypothesis(tst, partials, n_h, crit, results + th);
+    };
     while (item < n_items) {
         const unsigned pass = item / total;
         const unsigned c = item - pass * total;
@@ -1136,7 +1150,7 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
                 tma_next = stage_tile(g + (size_t)(t + 1) * kWTileFloats, min((unsigned)kWTile, n_pts - (t + 1) * kWTile), pts_end,
                                       tile0 + other * kWTileBytes, bar0 + 8 * other);
             } else {
-                // claim the next item only now: claiming earlier parks ~1 item per warp in front of the
+                // claim the next item only now: claiming a whole item earlier parks ~1 item per warp in front of the
                 // workers, which pushes them a pass ahead of their dependencies (measured: 2.21 -> 2.33 ms)
                 next_item = claim();
                 next_info = locate(next_item);
@@ -1154,6 +1168,9 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
             stage ^= 1;
             tma_cur = tma_next;
         };
+        // (tried, no gain: taking the arrival ticket one tile into the next item so that the release fence finds the
+        // partial stores already performed -- 1 % at chunk 3072 and a circular wait at chunk 4096; splitting the claim
+        // over the last two tiles to hide the atomic and the chunk-record load -- 1.50 -> 1.52 ms.)
         // (tried: issuing the gathers of group g+1 before consuming group g from a second register set.  It
         // does not overlap anything: ptxas tracks both sets on the same scoreboard, so the first consume
         // waits for the newest gathers as well -- measured 2.19 -> 2.39..2.54 ms.)
@@ -1174,11 +1191,7 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
             }
 #endif
             __stcg(partials + (size_t)c * kPartialStride + lane, mine);
-            __syncwarp();            // all 32 partial stores precede lane 0's release below
-            int is_last = 0;
-            if (lane == 0) is_last = (atom_add_release(&st->arrived, 1u) == __ldcg(&st->n_chunks) - 1) ? 1 : 0;
-            is_last = __shfl_sync(0xffffffffu, is_last, 0);
-            if (is_last) warp_finish_hypothesis(st, partials, info.w, crit, results + h);
+            take_ticket(st, info.w, h);
         }
         item = next_item;
         info = next_info;
@@ -1253,7 +1266,7 @@ template <class SceneT>
 int persistent_grid(int* grid_out) {
     static int cached = 0;
     if (!cached) {
-        const int smem = kPersistSmem;
+        const int smem = persist_smem<SceneT>();
         PR_CUDA_TRY(cudaFuncSetAttribute(icp_persistent_kernel<SceneT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ = 0, dev = 0, sms = 0;
         PR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_persistent_kernel<SceneT>, kPThreads, smem));
@@ -1263,6 +1276,16 @@ int persistent_grid(int* grid_out) {
     }
     *grid_out = cached;
     return PR_OK;
+}
+
+// Points per work item of the persistent driver.  Large items amortise the per-item cost (claim, reduction,
+// release fence, ticket: 4096 beats 2048 by 10 % on 512 hypotheses), but a pass must still consist of a
+// few items per resident warp or the warps run into the pass-to-pass dependency of their hypotheses
+// (8192: +30 %), and a small batch needs enough items to occupy the machine at all.
+inline uint32_t persist_chunk_points(size_t n_hyp, size_t capacity_points) {
+    uint32_t chunk = kPersistChunk;
+    while (chunk > 512 && capacity_points / chunk + n_hyp < (size_t)kNumSMs * kPWarps * 2) chunk >>= 1;
+    return chunk;
 }
 
 // SceneT: the scene as the per-pass driver consumes it; PScene: as the persistent driver consumes it
@@ -1287,9 +1310,10 @@ int run_icp(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_
         PR_LAUNCH_CHECK();
         return PR_OK;
     }
-    const size_t max_items = (capacity_points / kPersistChunk + n_hyp + 1) * (size_t)(crit.max_iteration + 1);
+    const uint32_t chunk_pts = persist_chunk_points(n_hyp, capacity_points);
+    const size_t max_items = (capacity_points / chunk_pts + n_hyp + 1) * (size_t)(crit.max_iteration + 1);
     if (max_items > 0x7FFFFFFFull) return PR_ERR_INVALID_ARGUMENT;
-    icp_plan_kernel<<<1, kIcpThreads, 0, stream>>>(counts_dev, (uint32_t)n_hyp, kPersistChunk, ws.state, ws.chunk_hyp,
+    icp_plan_kernel<<<1, kIcpThreads, 0, stream>>>(counts_dev, (uint32_t)n_hyp, chunk_pts, ws.state, ws.chunk_hyp,
                                                    (uint32_t)ws.max_chunks, &ws.ctl->total_chunks, results_dev, &ws.ctl->next_item,
                                                    offsets_dev, ws.chunk_info);
     int grid = 0;
@@ -1298,12 +1322,12 @@ int run_icp(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_
     grid = (int)std::min<size_t>((size_t)grid, (max_items + kPWarps - 1) / kPWarps);
     int threads = kPThreads;
     if (const char* e = getenv("PR_ICP_WARPS")) threads = std::max(1, std::min(kPWarps, atoi(e))) * 32;   // experiments
-    icp_persistent_kernel<PScene><<<grid, threads, kPersistSmem, stream>>>(
+    icp_persistent_kernel<PScene><<<grid, threads, persist_smem<PScene>(), stream>>>(
         pts_dev, capacity_points, ws.chunk_info, ws.ctl, ws.state, ws.partials, pscene, crit, results_dev);
     count_launch(2);
     if (flags & PR_ICP_UPDATE_POINTS) {
         icp_apply_kernel<<<kNumSMs * 4, 256, 0, stream>>>(pts_dev, offsets_dev, counts_dev, ws.chunk_hyp, &ws.ctl->total_chunks,
-                                                          kPersistChunk, ws.state);
+                                                          chunk_pts, ws.state);
         count_launch();
     }
     PR_LAUNCH_CHECK();

@@ -8,7 +8,7 @@ import importlib
 import pose_refine_b200
 bm = importlib.import_module('pose_refine_b200.build')
 bm = sys.modules['pose_refine_b200.build']
-VDIR = os.path.join(ROOT, "pose_refine_b200", "variants")
+VDIR = os.environ.get("VDIR", os.path.join(ROOT, "pose_refine_b200", "variants"))
 os.makedirs(VDIR, exist_ok=True)
 for f in ([] if os.environ.get("KEEP") else os.listdir(VDIR)):
     if f.endswith(".so"): os.remove(os.path.join(VDIR, f))

@@ -6,7 +6,7 @@ for f in pose_refine_b200/variants/lib_*.so; do
   for w in ${WARPS_LIST:-0}; do
     if [ "$w" = "0" ]; then unset PR_ICP_WARPS; else export PR_ICP_WARPS=$w; fi
     echo -n "{\"warps\": $w, \"r\": " >> gpurun_out/variants.jsonl
-    PR_LIB=$PWD/$f timeout 200 python scripts/time_icp.py 512 8 >> gpurun_out/variants.jsonl 2>> gpurun_out/variants.err
+    PR_LIB=$PWD/$f timeout 40 python scripts/time_icp.py 512 8 >> gpurun_out/variants.jsonl 2>> gpurun_out/variants.err
     echo "}" >> gpurun_out/variants.jsonl
   done
 done
