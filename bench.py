@@ -243,6 +243,7 @@ def run_ours(args):
     # Stages are called through the C ABI with buffers allocated once, exactly as pr_refiner does internally.
     roofline = stage = None
     cpu = None
+    ref_cuda = None
     if rank == 0:
         import ctypes as C
         L = _lib.lib()
@@ -320,6 +321,7 @@ def run_ours(args):
         del depth, pts, ws_r, ws_i
         if world == 1 and not args.no_cpu:
             cpu = cpu_pipeline("reference", mesh, scene_pose, poses, target_s=args.cpu_seconds)
+            ref_cuda = ref_cuda_build(min(P, 256))
 
     if rank == 0:
         total_hyp = P * world * args.steps
@@ -337,10 +339,36 @@ def run_ours(args):
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
+        if ref_cuda is not None:
+            out["ref_cuda_build"] = ref_cuda
         print(json.dumps(out), flush=True)
     ref.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def ref_cuda_build(n_hyp):
+    """The reference's own CUDA path (render_cuda_keep_in_gpu -> depth2cloud_cuda -> ICP_Point2Plane_cuda per hypothesis,
+    oracle/_ref/libpose_refine_refcuda.so = its .cu files compiled unmodified for sm_100) timed on this GPU on a bounded
+    sample of the same workload, in a child process (scripts/time_ref_cuda.py).  Reported next to cpu_baseline; it is the
+    "reference CUDA build" of north_star's 10x target.  None when the library was not built."""
+    import subprocess
+    script = os.path.join(ROOT, "scripts", "time_ref_cuda.py")
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpose_refine_refcuda.so")):
+        return None
+    try:
+        r = subprocess.run([sys.executable, script, str(n_hyp), "1,8"], capture_output=True, text=True, timeout=240)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        runs = [x for x in d.get("runs", []) if "hyp_per_s" in x]
+        if not runs:
+            return {"unavailable": "reference CUDA build failed to run", "detail": r.stderr[-200:]}
+        top = max(runs, key=lambda x: x["hyp_per_s"])
+        return {"value": top["hyp_per_s"], "unit": "hypotheses/s", "host_threads": top["threads"],
+                "serial_value": next((x["hyp_per_s"] for x in runs if x["threads"] == 1), None),
+                "sample": f"{n_hyp} hypotheses of the same workload, best of 1 / 8 host threads (reference README recipe)",
+                "pose_max_abs_diff_vs_ours_converged": top.get("pose_max_abs_diff_vs_ours_converged")}
+    except Exception as e:      # a measurement aid must never take the bench line down
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
 
 def main():
