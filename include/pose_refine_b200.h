@@ -130,6 +130,21 @@ int pr_render_indexed_batch(const float* verts_dev, size_t n_verts, const int32_
                             const float proj[16], pr_roi roi, int32_t* out_depth_dev,
                             void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
 
+/* Fused render -> cloud: render_cuda_keep_in_gpu (renderer.cu:269-303) followed by depth2cloud_cuda           */
+/* (icp.cu:256-286) for every pose, which is how the reference's own pipeline chains them (test.cpp:143-153).  */
+/* The rasteriser's tile write-out counts the valid pixels, so the clouds are built from one more read of the   */
+/* non-empty tiles only.  out_depth_dev is the same int32 batch pr_render_indexed_batch writes.  Cloud i is     */
+/* out_pts_dev[3*offsets[i] .. 3*(offsets[i]+counts[i])): the same points depth2cloud_cuda produces, ordered     */
+/* tile by tile (64x32-pixel screen tiles in row-major order, row-major inside a tile) instead of row-major      */
+/* over the image.  counts / offsets / overflow / capacity_points / align_points as in pr_depth2cloud_count.     */
+size_t pr_render_cloud_workspace_bytes(size_t n_poses, size_t n_verts, size_t n_tris, size_t width, size_t height);
+int pr_render_cloud_batch(const float* verts_dev, size_t n_verts, const int32_t* faces_dev, size_t n_tris,
+                          const float* poses, int poses_on_device, size_t n_poses, size_t width, size_t height,
+                          const float proj[16], const float K[9], int32_t* out_depth_dev,
+                          float* out_pts_dev, size_t capacity_points, uint32_t align_points,
+                          uint32_t* counts_dev, uint32_t* offsets_dev, uint32_t* overflow_dev,
+                          void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
+
 /* raw2depth_uint16_cuda / raw2mask_uint8_cuda / raw2depth_mask_cuda (renderer.cu:338-439):      */
 /* depth = uint16_t(raw), mask = raw > 0 ? 255 : 0.  Either output may be NULL.                  */
 int pr_raw2depth_mask(const int32_t* raw_dev, size_t n, uint16_t* depth_dev, uint8_t* mask_dev, pr_stream_t stream);

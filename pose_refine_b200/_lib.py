@@ -43,6 +43,9 @@ PROTOTYPES = {
     "pr_mesh_index": (_i, [_vp, _sz, _vp, _vp, C.POINTER(_sz)]),
     "pr_render_indexed_workspace_bytes": (_sz, [_sz, _sz, _sz, _sz, _sz]),
     "pr_render_indexed_batch": (_i, [_vp, _sz, _vp, _sz, _vp, _i, _sz, _sz, _sz, _vp, Roi, _vp, _vp, _sz, _vp]),
+    "pr_render_cloud_workspace_bytes": (_sz, [_sz, _sz, _sz, _sz, _sz]),
+    "pr_render_cloud_batch": (_i, [_vp, _sz, _vp, _sz, _vp, _i, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _sz, _u32, _vp, _vp, _vp,
+                                   _vp, _sz, _vp]),
     "pr_raw2depth_mask": (_i, [_vp, _sz, _vp, _vp, _vp]),
     "pr_depth2cloud_workspace_bytes": (_sz, [_sz, _u32, _u32]),
     "pr_depth2cloud_count": (_i, [_vp, _i, _sz, _u32, _u32, _u32, _u32, _sz, _vp, _vp, _vp, _vp, _sz, _vp]),

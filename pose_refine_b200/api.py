@@ -168,6 +168,32 @@ def render_indexed_keep_in_gpu(verts, faces, poses, width, height, proj_mat, roi
     return out
 
 
+def render_cloud_batch(verts, faces, poses, width, height, proj_mat, K, capacity_points=None, align_points=4):
+    """Fused render_cuda_keep_in_gpu + depth2cloud_cuda per pose (pr_render_cloud_batch).
+    -> (depth [P,H,W] int32, pts [cap,3] float32, offsets [P+1] int32, counts [P] int32), all on the device.
+    Cloud i = pts[offsets[i] : offsets[i] + counts[i]], the points of depth2cloud in screen-tile order."""
+    _require_device()
+    verts = _dev(verts, torch.float32).reshape(-1, 3)
+    faces = _dev(faces, torch.int32).reshape(-1, 3)
+    proj = _f32c(proj_mat).reshape(16)
+    Kc = _f32c(K).reshape(9)
+    poses_t = _dev(poses, torch.float32).reshape(-1, 16)
+    n_poses = poses_t.shape[0]
+    depth = torch.empty((n_poses, height, width), dtype=torch.int32, device="cuda")
+    cap = int(capacity_points) if capacity_points is not None else n_poses * width * height
+    pts = torch.empty((cap + 8, 3), dtype=torch.float32, device="cuda")
+    counts = torch.empty(n_poses, dtype=torch.int32, device="cuda")
+    offsets = torch.empty(n_poses + 1, dtype=torch.int32, device="cuda")
+    overflow = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ws_bytes = lib().pr_render_cloud_workspace_bytes(n_poses, verts.shape[0], faces.shape[0], width, height)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    check(lib().pr_render_cloud_batch(verts.data_ptr(), verts.shape[0], faces.data_ptr(), faces.shape[0], poses_t.data_ptr(), 1,
+                                      n_poses, width, height, proj.ctypes.data, Kc.ctypes.data, depth.data_ptr(), pts.data_ptr(),
+                                      cap, align_points, counts.data_ptr(), offsets.data_ptr(), overflow.data_ptr(),
+                                      ws.data_ptr(), ws_bytes, _stream()), "pr_render_cloud_batch")
+    return depth, pts, offsets, counts
+
+
 def render_cuda(tris, poses, width, height, proj_mat, roi=(0, 0, 0, 0)):
     """-> host int32 array (renderer.cu:189-267)."""
     return render_cuda_keep_in_gpu(tris, poses, width, height, proj_mat, roi).cpu().numpy()

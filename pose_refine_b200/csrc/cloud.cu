@@ -88,16 +88,17 @@ __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* s_warp
 
 // one CTA per image: seg counts -> exclusive offsets (in place), counts[image] = total
 __global__ void __launch_bounds__(kSegThreads)
-cloud_scan_kernel(uint32_t* __restrict__ seg, uint32_t n_seg, uint32_t* __restrict__ counts) {
+cloud_scan_kernel(const uint32_t* seg_in, uint32_t* seg_out, uint32_t n_seg, uint32_t* __restrict__ counts) {
     __shared__ unsigned s_warp[kSegThreads / 32];
-    uint32_t* s = seg + (size_t)blockIdx.x * n_seg;
+    const uint32_t* s = seg_in + (size_t)blockIdx.x * n_seg;
+    uint32_t* o = seg_out + (size_t)blockIdx.x * n_seg;      // may alias seg_in
     unsigned carry = 0;
     for (uint32_t b = 0; b < n_seg; b += kSegThreads) {
         const uint32_t i = b + threadIdx.x;
         const unsigned v = (i < n_seg) ? s[i] : 0u;
         unsigned total;
         const unsigned excl = block_excl_scan(v, s_warp, &total);
-        if (i < n_seg) s[i] = carry + excl;
+        if (i < n_seg) o[i] = carry + excl;
         carry += total;
     }
     if (threadIdx.x == 0) counts[blockIdx.x] = carry;
@@ -170,7 +171,80 @@ cloud_fill_kernel(const T* __restrict__ depth, uint32_t width, uint32_t n_px, ui
     }
 }
 
+// Fill from screen tiles (the refiner's fused render -> cloud path): one CTA per (tile, image); a tile without valid
+// pixels returns before touching the depth image, so only the ~10 % of tiles the object covers are read again
+// (the segment-based pass above reads every pixel of every image twice).  Points of an image are ordered tile by
+// tile (row-major tiles, row-major pixels inside a tile) -- deterministic, but NOT depth2cloud_cuda's row-major
+// order; the coordinates themselves are the same values.  Tile = 64 x 32 pixels = kSegPx, 8 pixels per thread.
+__global__ void __launch_bounds__(kSegThreads)
+cloud_fill_tiles_kernel(const int32_t* __restrict__ depth, uint32_t width, uint32_t height, int tiles_x,
+                        const unsigned* __restrict__ tile_valid, const unsigned* __restrict__ tile_off,
+                        const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts, Intrinsics K,
+                        float* __restrict__ out, size_t capacity) {
+    __shared__ unsigned s_warp[kSegThreads / 32];
+    const uint32_t image = blockIdx.y, tile = blockIdx.x;
+    const size_t t_idx = (size_t)image * gridDim.x + tile;
+    if (tile_valid[t_idx] == 0 || counts[image] == 0) return;     // counts == 0: the cloud did not fit (overflow)
+    const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const uint32_t v = ty * 32 + (threadIdx.x >> 3);              // 8 threads per tile row
+    const uint32_t u0 = tx * 64 + (threadIdx.x & 7) * 8;
+    const int32_t* img = depth + (size_t)image * width * height;
+    int d[kPxPerThread];
+    unsigned c = 0;
+#pragma unroll
+    for (int k = 0; k < kPxPerThread; k++) d[k] = 0;
+    if (v < height) {
+        const int32_t* row = img + (size_t)v * width;
+        if (u0 + kPxPerThread <= width && ((reinterpret_cast<uintptr_t>(row + u0) & 15) == 0)) {
+            const int4 a = __ldg(reinterpret_cast<const int4*>(row + u0));
+            const int4 b = __ldg(reinterpret_cast<const int4*>(row + u0) + 1);
+            d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPxPerThread; k++) d[k] = (u0 + k < width) ? row[u0 + k] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < kPxPerThread; k++) c += (d[k] > 0) ? 1u : 0u;
+    }
+    unsigned total;
+    const unsigned excl = block_excl_scan(c, s_warp, &total);
+    if (c == 0) return;
+    size_t dst = (size_t)offsets[image] + tile_off[t_idx] + excl;
+#pragma unroll
+    for (int k = 0; k < kPxPerThread; k++) {
+        if (d[k] > 0) {
+            if (dst < capacity) {
+                // icp.cu:249-251
+                const float z = divf((float)d[k], 1000.0f);
+                const float x = mulf(divf(subf((float)(u0 + k), K.cx), K.fx), z);
+                const float y = mulf(divf(subf((float)v, K.cy), K.fy), z);
+                out[3 * dst + 0] = x; out[3 * dst + 1] = y; out[3 * dst + 2] = z;
+            }
+            dst++;
+        }
+    }
+}
+
 inline size_t cloud_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int cloud_from_tiles(const int32_t* depth_dev, size_t n_images, uint32_t width, uint32_t height, const float K[9],
+                     int tile_w, int tile_h, int tiles_x, int tiles_y, const unsigned* tile_valid, unsigned* tile_off,
+                     uint32_t* counts_dev, uint32_t* offsets_dev, uint32_t* overflow_dev, size_t capacity_points,
+                     uint32_t align_points, float* out_pts_dev, cudaStream_t stream) {
+    if (tile_w != 64 || tile_h != 32) return PR_ERR_UNSUPPORTED;       // the fill kernel's thread -> pixel map
+    const uint32_t n_tiles = (uint32_t)(tiles_x * tiles_y);
+    cloud_scan_kernel<<<(unsigned)n_images, kSegThreads, 0, stream>>>(tile_valid, tile_off, n_tiles, counts_dev);
+    cloud_offsets_kernel<<<1, kSegThreads, 0, stream>>>(counts_dev, (uint32_t)n_images, align_points,
+                                                        capacity_points ? (unsigned long long)capacity_points : ~0ull,
+                                                        offsets_dev, overflow_dev);
+    const Intrinsics Ki = {K[0], K[4], K[2], K[5]};
+    cloud_fill_tiles_kernel<<<dim3(n_tiles, (unsigned)n_images), kSegThreads, 0, stream>>>(
+        depth_dev, width, height, tiles_x, tile_valid, tile_off, offsets_dev, counts_dev, Ki, out_pts_dev,
+        capacity_points ? capacity_points : ~(size_t)0);
+    count_launch(3);
+    PR_LAUNCH_CHECK();
+    return PR_OK;
+}
 
 }  // namespace prb
 
@@ -202,7 +276,7 @@ int pr_depth2cloud_count(const void* depth_dev, int depth_is_int32, size_t n_ima
     const dim3 grid(n_seg, (unsigned)n_images);
     if (depth_is_int32) cloud_count_kernel<int32_t><<<grid, kSegThreads, 0, stream>>>((const int32_t*)depth_dev, (uint32_t)n_px, n_seg, seg, vec);
     else cloud_count_kernel<uint16_t><<<grid, kSegThreads, 0, stream>>>((const uint16_t*)depth_dev, (uint32_t)n_px, n_seg, seg, vec);
-    cloud_scan_kernel<<<(unsigned)n_images, kSegThreads, 0, stream>>>(seg, n_seg, counts_dev);
+    cloud_scan_kernel<<<(unsigned)n_images, kSegThreads, 0, stream>>>(seg, seg, n_seg, counts_dev);
     cloud_offsets_kernel<<<1, kSegThreads, 0, stream>>>(counts_dev, (uint32_t)n_images, align_points,
                                                         capacity_points ? (unsigned long long)capacity_points : ~0ull,
                                                         offsets_dev, overflow_dev);

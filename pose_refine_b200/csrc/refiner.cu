@@ -52,14 +52,11 @@ int run_device(pr_refiner* r, const float* poses_dev, size_t n_hyp, pr_icp_crite
                pr_registration_result* results_dev, cudaStream_t stream) {
     pr_stream_t s = reinterpret_cast<pr_stream_t>(stream);
     pr_roi none = {0, 0, 0, 0};
-    int rc = pr_render_indexed_batch(r->d_verts, r->n_verts, r->d_faces, r->n_tris, poses_dev, 1, n_hyp, r->W, r->H, r->proj, none,
-                                     r->d_depth, r->ws_render, r->ws_render_bytes, s);
-    if (rc != PR_OK) return rc;
-    rc = pr_depth2cloud_count(r->d_depth, 1, n_hyp, r->W, r->H, 1, 4, r->capacity_points, r->d_counts, r->d_offsets,
-                              r->d_overflow, r->ws_cloud, r->ws_cloud_bytes, s);
-    if (rc != PR_OK) return rc;
-    rc = pr_depth2cloud_fill(r->d_depth, 1, n_hyp, r->W, r->H, r->K, 1, 0, 0, r->d_offsets, r->d_pts, r->capacity_points,
-                             r->ws_cloud, r->ws_cloud_bytes, s);
+    // render + clouds in one pass over the depth batch (tile-ordered clouds; the reduction does not care about order)
+    int rc = pr_render_cloud_batch(r->d_verts, r->n_verts, r->d_faces, r->n_tris, poses_dev, 1, n_hyp, r->W, r->H, r->proj, r->K,
+                                   r->d_depth, r->d_pts, r->capacity_points, 4, r->d_counts, r->d_offsets, r->d_overflow,
+                                   r->ws_render, r->ws_render_bytes, s);
+    (void)none;
     if (rc != PR_OK) return rc;
     if (r->scene_kind == 0)
         return pr_icp_projective_batch(r->d_pts, r->d_offsets, r->d_counts, n_hyp, r->capacity_points, &r->sp, crit, results_dev, 0,
@@ -139,7 +136,7 @@ int pr_refiner_create(pr_refiner** out, const float* tris_host, size_t n_tris, u
     std::vector<int32_t> faces(n_tris * 3);
     rc = pr_mesh_index(tris_host, n_tris, verts.data(), faces.data(), &r->n_verts);
     if (rc != PR_OK) { delete r; return rc; }
-    r->ws_render_bytes = pr_render_indexed_workspace_bytes(max_hyp, r->n_verts, n_tris, width, height);
+    r->ws_render_bytes = pr_render_cloud_workspace_bytes(max_hyp, r->n_verts, n_tris, width, height);
     r->ws_cloud_bytes = pr_depth2cloud_workspace_bytes(max_hyp, width, height);
     r->ws_icp_bytes = pr_icp_workspace_bytes(max_hyp, r->capacity_points, 3 * n_px + 16);   // projective: n_px; kd-tree: <= n_px points + 2 * (2 n_px + 1) nodes... bounded by 3 n_px for leaf >= 2
     cudaError_t e = cudaSuccess;

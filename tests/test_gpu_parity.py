@@ -118,6 +118,40 @@ def test_render_indexed_mesh_bit_exact(api, port, mesh, golden):
     assert np.array_equal(got, port.render(tris, poses, 640, 480, arrays["proj"]))
 
 
+def test_render_cloud_fused_matches_render_then_depth2cloud(api, port, mesh, golden):
+    """pr_render_cloud_batch: the depth batch is the rasteriser's, bit for bit; every cloud holds exactly the points
+    depth2cloud_cpu (icp.cpp:73-117) makes from that depth image (same float values), in screen-tile order; offsets are
+    aligned; an odd image size (partial tiles at the right and bottom edge) and an empty pose are covered."""
+    arrays, scal = golden
+    K = arrays["K"]
+    verts, faces = api.mesh_index(mesh)
+    poses = arrays["hyp8"].copy()
+    poses[5, 2, 3] = -500.0                                   # object behind the camera: empty depth, empty cloud
+    for (W, H, proj, Kc) in [(640, 480, arrays["proj"], K), (161, 121, arrays["proj_small"], arrays["K_small"])]:
+        depth, pts, offsets, counts = api.render_cloud_batch(verts, faces, poses, W, H, proj, Kc)
+        depth, pts, offsets, counts = depth.cpu().numpy(), pts.cpu().numpy(), offsets.cpu().numpy(), counts.cpu().numpy()
+        want_depth = port.render(mesh, poses, W, H, proj)
+        assert np.array_equal(depth, want_depth)
+        assert counts[5] == 0 and np.all(offsets % 4 == 0) and offsets[-1] >= offsets[-2] + counts[-1]
+        for i in range(len(poses)):
+            want = port.depth2cloud(want_depth[i], Kc)
+            got = pts[offsets[i]: offsets[i] + counts[i]]
+            assert counts[i] == want.shape[0], (i, counts[i], want.shape)
+            # same multiset of points: sort both by (y, x) -- within an image the (x, y) pair identifies the pixel
+            ks, kg = np.lexsort((want[:, 0], want[:, 1])), np.lexsort((got[:, 0], got[:, 1]))
+            assert np.array_equal(want[ks], got[kg]), f"pose {i}: fused cloud differs from depth2cloud of the same depth"
+            if W == 640 and counts[i]:
+                # tile order: the first point lies in the first non-empty 64x32 tile (row-major tiles)
+                ys, xs = np.nonzero(want_depth[i])
+                tiles = (ys // 32) * 10 + xs // 64
+                first = tiles.min()
+                sel = tiles == first
+                y0, x0 = ys[sel].min(), None
+                x0 = xs[sel & (ys == y0)].min()
+                z = np.float32(want_depth[i][y0, x0]) / np.float32(1000.0)
+                assert got[0, 2] == z
+
+
 def test_render_big_triangles_overflowing_bins(api, port, golden):
     """A few screen-filling triangles: every tile lists them; the per-pose list capacity still holds,
     and with a deliberately tiny workspace the overflow fallback must give the same image."""
