@@ -171,21 +171,54 @@ cloud_fill_kernel(const T* __restrict__ depth, uint32_t width, uint32_t n_px, ui
     }
 }
 
-// Fill from screen tiles (the refiner's fused render -> cloud path): one CTA per (tile, image); a tile without valid
-// pixels returns before touching the depth image, so only the ~10 % of tiles the object covers are read again
-// (the segment-based pass above reads every pixel of every image twice).  Points of an image are ordered tile by
+// one CTA per image: tile counts -> exclusive offsets, image total, and the compact list of its non-empty tiles
+__global__ void __launch_bounds__(kSegThreads)
+tile_scan_kernel(const uint32_t* __restrict__ tile_valid, uint32_t* __restrict__ tile_off, uint32_t n_tiles,
+                 uint32_t* __restrict__ counts, uint32_t* __restrict__ tile_list, uint32_t* __restrict__ n_list) {
+    __shared__ unsigned s_warp[kSegThreads / 32];
+    const uint32_t* s = tile_valid + (size_t)blockIdx.x * n_tiles;
+    uint32_t* o = tile_off + (size_t)blockIdx.x * n_tiles;
+    uint32_t* l = tile_list + (size_t)blockIdx.x * n_tiles;
+    unsigned carry = 0, lcarry = 0;
+    for (uint32_t b = 0; b < n_tiles; b += kSegThreads) {
+        const uint32_t i = b + threadIdx.x;
+        const unsigned v = (i < n_tiles) ? s[i] : 0u;
+        unsigned total, ltotal;
+        const unsigned excl = block_excl_scan(v, s_warp, &total);
+        const unsigned lexcl = block_excl_scan(v ? 1u : 0u, s_warp, &ltotal);
+        if (i < n_tiles) o[i] = carry + excl;
+        if (v) l[lcarry + lexcl] = i;
+        carry += total; lcarry += ltotal;
+    }
+    if (threadIdx.x == 0) { counts[blockIdx.x] = carry; n_list[blockIdx.x] = lcarry; }
+}
+
+// Fill from screen tiles (the refiner's fused render -> cloud path): kFillCtas CTAs per image walk the image's list of
+// non-empty tiles, so only the ~10 % of tiles the object covers are read again (the segment-based pass above reads
+// every pixel of every image twice, and a grid with one CTA per tile spends its time launching 70k empty CTAs).  Points of an image are ordered tile by
 // tile (row-major tiles, row-major pixels inside a tile) -- deterministic, but NOT depth2cloud_cuda's row-major
 // order; the coordinates themselves are the same values.  Tile = 64 x 32 pixels = kSegPx, 8 pixels per thread.
+constexpr int kFillCtas = 16;
 __global__ void __launch_bounds__(kSegThreads)
-cloud_fill_tiles_kernel(const int32_t* __restrict__ depth, uint32_t width, uint32_t height, int tiles_x,
-                        const unsigned* __restrict__ tile_valid, const unsigned* __restrict__ tile_off,
+cloud_fill_tiles_kernel(const int32_t* __restrict__ depth, uint32_t width, uint32_t height, int tiles_x, uint32_t n_tiles,
+                        const unsigned* __restrict__ tile_list, const unsigned* __restrict__ n_list,
+                        const unsigned* __restrict__ tile_off,
                         const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts, Intrinsics K,
                         float* __restrict__ out, size_t capacity) {
     __shared__ unsigned s_warp[kSegThreads / 32];
-    const uint32_t image = blockIdx.y, tile = blockIdx.x;
-    const size_t t_idx = (size_t)image * gridDim.x + tile;
-    if (tile_valid[t_idx] == 0 || counts[image] == 0) return;     // counts == 0: the cloud did not fit (overflow)
+    __shared__ float s_fx[64], s_fy[32];                          // (u - cx) / fx per tile column, (v - cy) / fy per tile row
+    const uint32_t image = blockIdx.y;
+    if (counts[image] == 0) return;                               // empty, or the cloud did not fit (overflow)
+    const uint32_t n_here = n_list[image];
+  for (uint32_t li = blockIdx.x; li < n_here; li += gridDim.x) {
+    const uint32_t tile = tile_list[(size_t)image * n_tiles + li];
+    const size_t t_idx = (size_t)image * n_tiles + tile;
     const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    // the two pixel-only factors of icp.cu:250-251, one IEEE division per thread instead of two per point
+    __syncthreads();
+    if (threadIdx.x < 64) s_fx[threadIdx.x] = divf(subf((float)(tx * 64 + threadIdx.x), K.cx), K.fx);
+    else if (threadIdx.x < 96) s_fy[threadIdx.x - 64] = divf(subf((float)(ty * 32 + threadIdx.x - 64), K.cy), K.fy);
+    __syncthreads();
     const uint32_t v = ty * 32 + (threadIdx.x >> 3);              // 8 threads per tile row
     const uint32_t u0 = tx * 64 + (threadIdx.x & 7) * 8;
     const int32_t* img = depth + (size_t)image * width * height;
@@ -208,7 +241,6 @@ cloud_fill_tiles_kernel(const int32_t* __restrict__ depth, uint32_t width, uint3
     }
     unsigned total;
     const unsigned excl = block_excl_scan(c, s_warp, &total);
-    if (c == 0) return;
     size_t dst = (size_t)offsets[image] + tile_off[t_idx] + excl;
 #pragma unroll
     for (int k = 0; k < kPxPerThread; k++) {
@@ -216,13 +248,14 @@ cloud_fill_tiles_kernel(const int32_t* __restrict__ depth, uint32_t width, uint3
             if (dst < capacity) {
                 // icp.cu:249-251
                 const float z = divf((float)d[k], 1000.0f);
-                const float x = mulf(divf(subf((float)(u0 + k), K.cx), K.fx), z);
-                const float y = mulf(divf(subf((float)v, K.cy), K.fy), z);
+                const float x = mulf(s_fx[(threadIdx.x & 7) * 8 + k], z);
+                const float y = mulf(s_fy[threadIdx.x >> 3], z);
                 out[3 * dst + 0] = x; out[3 * dst + 1] = y; out[3 * dst + 2] = z;
             }
             dst++;
         }
     }
+  }
 }
 
 inline size_t cloud_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -233,13 +266,16 @@ int cloud_from_tiles(const int32_t* depth_dev, size_t n_images, uint32_t width, 
                      uint32_t align_points, float* out_pts_dev, cudaStream_t stream) {
     if (tile_w != 64 || tile_h != 32) return PR_ERR_UNSUPPORTED;       // the fill kernel's thread -> pixel map
     const uint32_t n_tiles = (uint32_t)(tiles_x * tiles_y);
-    cloud_scan_kernel<<<(unsigned)n_images, kSegThreads, 0, stream>>>(tile_valid, tile_off, n_tiles, counts_dev);
+    // scratch behind the offsets: list of non-empty tiles per image, then the list lengths (see cloud_tiles_scratch_words)
+    unsigned* tile_list = tile_off + n_images * (size_t)n_tiles;
+    unsigned* n_list = tile_list + n_images * (size_t)n_tiles;
+    tile_scan_kernel<<<(unsigned)n_images, kSegThreads, 0, stream>>>(tile_valid, tile_off, n_tiles, counts_dev, tile_list, n_list);
     cloud_offsets_kernel<<<1, kSegThreads, 0, stream>>>(counts_dev, (uint32_t)n_images, align_points,
                                                         capacity_points ? (unsigned long long)capacity_points : ~0ull,
                                                         offsets_dev, overflow_dev);
     const Intrinsics Ki = {K[0], K[4], K[2], K[5]};
-    cloud_fill_tiles_kernel<<<dim3(n_tiles, (unsigned)n_images), kSegThreads, 0, stream>>>(
-        depth_dev, width, height, tiles_x, tile_valid, tile_off, offsets_dev, counts_dev, Ki, out_pts_dev,
+    cloud_fill_tiles_kernel<<<dim3(kFillCtas, (unsigned)n_images), kSegThreads, 0, stream>>>(
+        depth_dev, width, height, tiles_x, n_tiles, tile_list, n_list, tile_off, offsets_dev, counts_dev, Ki, out_pts_dev,
         capacity_points ? capacity_points : ~(size_t)0);
     count_launch(3);
     PR_LAUNCH_CHECK();

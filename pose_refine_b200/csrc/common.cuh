@@ -48,7 +48,9 @@ struct alignas(16) Mat34 {  // rows 0..2 of a row-major 4x4 rigid transform
 };
 
 // cloud.cu: compacted clouds of a depth batch from per-tile valid-pixel counts (the rasteriser's tiles), tile-major
-// point order; tile_valid: n_images * tiles_x * tiles_y counts (in), tile_off: same size (scratch).
+// point order; tile_valid: n_images * tiles_x * tiles_y counts (in); tile_off: scratch of
+// cloud_tiles_scratch_words(n_images, tiles) words (offsets, non-empty tile lists, list lengths).
+inline size_t cloud_tiles_scratch_words(size_t n_images, size_t n_tiles) { return 2 * n_images * n_tiles + n_images; }
 int cloud_from_tiles(const int32_t* depth_dev, size_t n_images, uint32_t width, uint32_t height, const float K[9],
                      int tile_w, int tile_h, int tiles_x, int tiles_y, const unsigned* tile_valid, unsigned* tile_off,
                      uint32_t* counts_dev, uint32_t* offsets_dev, uint32_t* overflow_dev, size_t capacity_points,

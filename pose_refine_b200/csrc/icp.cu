@@ -777,9 +777,10 @@ __device__ __forceinline__ void sts32(unsigned addr, float v) {
 __device__ __forceinline__ void load_rec(const PackedScene& s, int idx, float4& A, float2& B) {
     const float4* r = s.rec + 2 * (size_t)(unsigned)idx;
 #if PR_REC == 2
-    float u0, u1;
+    float u0 = 0.f, u1 = 0.f;       // padding words of the record
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(A.x), "=f"(A.y), "=f"(A.z), "=f"(A.w), "=f"(B.x), "=f"(B.y), "=f"(u0), "=f"(u1) : "l"(r));
+    (void)u0; (void)u1;
 #else
     A = __ldg(r);
     B = __ldg(reinterpret_cast<const float2*>(r + 1));

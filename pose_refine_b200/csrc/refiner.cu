@@ -51,12 +51,10 @@ void free_scene(pr_refiner* r) {
 int run_device(pr_refiner* r, const float* poses_dev, size_t n_hyp, pr_icp_criteria crit,
                pr_registration_result* results_dev, cudaStream_t stream) {
     pr_stream_t s = reinterpret_cast<pr_stream_t>(stream);
-    pr_roi none = {0, 0, 0, 0};
     // render + clouds in one pass over the depth batch (tile-ordered clouds; the reduction does not care about order)
     int rc = pr_render_cloud_batch(r->d_verts, r->n_verts, r->d_faces, r->n_tris, poses_dev, 1, n_hyp, r->W, r->H, r->proj, r->K,
                                    r->d_depth, r->d_pts, r->capacity_points, 4, r->d_counts, r->d_offsets, r->d_overflow,
                                    r->ws_render, r->ws_render_bytes, s);
-    (void)none;
     if (rc != PR_OK) return rc;
     if (r->scene_kind == 0)
         return pr_icp_projective_batch(r->d_pts, r->d_offsets, r->d_counts, n_hyp, r->capacity_points, &r->sp, crit, results_dev, 0,
