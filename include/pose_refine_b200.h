@@ -137,12 +137,26 @@ int pr_render_indexed_batch(const float* verts_dev, size_t n_verts, const int32_
 /* out_pts_dev[3*offsets[i] .. 3*(offsets[i]+counts[i])): the same points depth2cloud_cuda produces, ordered     */
 /* tile by tile (64x32-pixel screen tiles in row-major order, row-major inside a tile) instead of row-major      */
 /* over the image.  counts / offsets / overflow / capacity_points / align_points as in pr_depth2cloud_count.     */
+/* Optional acceleration structure for it (no upstream counterpart): pr_mesh_cluster (host) reorders the faces of an   */
+/* indexed mesh along a Morton curve of their centroids, cuts them into clusters of 64 consecutive triangles and       */
+/* lists every cluster's unique vertices.  With the lists on the device (pr_mesh_clusters) the rasteriser bins          */
+/* clusters instead of triangles; the rendered depth is unchanged (depth is order independent).                         */
+/*   faces_inout       n_tris * 3 indices, reordered in place                                                            */
+/*   cluster_vert_off  room for (n_tris + 63) / 64 + 1 entries;  cluster_verts  room for 3 * n_tris entries              */
+typedef struct pr_mesh_clusters {
+    size_t n_clusters;
+    const int32_t* vert_off_dev;   /* n_clusters + 1 */
+    const int32_t* verts_dev;      /* vert_off[n_clusters] vertex ids */
+} pr_mesh_clusters;
+int pr_mesh_cluster(const float* verts_host, size_t n_verts, int32_t* faces_inout, size_t n_tris,
+                    int32_t* cluster_vert_off, int32_t* cluster_verts, size_t* n_clusters);
 size_t pr_render_cloud_workspace_bytes(size_t n_poses, size_t n_verts, size_t n_tris, size_t width, size_t height);
 int pr_render_cloud_batch(const float* verts_dev, size_t n_verts, const int32_t* faces_dev, size_t n_tris,
                           const float* poses, int poses_on_device, size_t n_poses, size_t width, size_t height,
                           const float proj[16], const float K[9], int32_t* out_depth_dev,
                           float* out_pts_dev, size_t capacity_points, uint32_t align_points,
                           uint32_t* counts_dev, uint32_t* offsets_dev, uint32_t* overflow_dev,
+                          const pr_mesh_clusters* clusters /* nullable; faces must then be pr_mesh_cluster's order */,
                           void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
 
 /* raw2depth_uint16_cuda / raw2mask_uint8_cuda / raw2depth_mask_cuda (renderer.cu:338-439):      */

@@ -23,6 +23,10 @@ class SceneNN(C.Structure):  # pr_scene_nn
                 ("nodes_dev", C.c_void_p), ("n_points", C.c_uint64), ("n_nodes", C.c_uint64)]
 
 
+class MeshClusters(C.Structure):  # pr_mesh_clusters
+    _fields_ = [("n_clusters", C.c_size_t), ("vert_off_dev", C.c_void_p), ("verts_dev", C.c_void_p)]
+
+
 _vp, _sz, _i, _u32, _f = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_float
 _fp = C.POINTER(C.c_float)
 
@@ -44,8 +48,9 @@ PROTOTYPES = {
     "pr_render_indexed_workspace_bytes": (_sz, [_sz, _sz, _sz, _sz, _sz]),
     "pr_render_indexed_batch": (_i, [_vp, _sz, _vp, _sz, _vp, _i, _sz, _sz, _sz, _vp, Roi, _vp, _vp, _sz, _vp]),
     "pr_render_cloud_workspace_bytes": (_sz, [_sz, _sz, _sz, _sz, _sz]),
+    "pr_mesh_cluster": (_i, [_vp, _sz, _vp, _sz, _vp, _vp, C.POINTER(_sz)]),
     "pr_render_cloud_batch": (_i, [_vp, _sz, _vp, _sz, _vp, _i, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _sz, _u32, _vp, _vp, _vp,
-                                   _vp, _sz, _vp]),
+                                   _vp, _vp, _sz, _vp]),
     "pr_raw2depth_mask": (_i, [_vp, _sz, _vp, _vp, _vp]),
     "pr_depth2cloud_workspace_bytes": (_sz, [_sz, _u32, _u32]),
     "pr_depth2cloud_count": (_i, [_vp, _i, _sz, _u32, _u32, _u32, _u32, _sz, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -168,8 +168,24 @@ def render_indexed_keep_in_gpu(verts, faces, poses, width, height, proj_mat, roi
     return out
 
 
-def render_cloud_batch(verts, faces, poses, width, height, proj_mat, K, capacity_points=None, align_points=4):
+def mesh_cluster(verts, faces):
+    """pr_mesh_cluster (host): Morton-ordered faces + per-cluster unique vertex lists.
+    -> (faces [T,3] int32 reordered, vert_off [C+1] int32, cluster_verts [n] int32)"""
+    verts = _f32c(verts).reshape(-1, 3)
+    faces = np.ascontiguousarray(faces, dtype=np.int32).reshape(-1, 3).copy()
+    T = faces.shape[0]
+    off = np.zeros((T + 63) // 64 + 1, np.int32)
+    cv = np.zeros(3 * T, np.int32)
+    n = C.c_size_t()
+    check(lib().pr_mesh_cluster(verts.ctypes.data, verts.shape[0], faces.ctypes.data, T, off.ctypes.data, cv.ctypes.data, C.byref(n)),
+          "pr_mesh_cluster")
+    off = off[: n.value + 1].copy()
+    return faces, off, cv[: off[-1]].copy()
+
+
+def render_cloud_batch(verts, faces, poses, width, height, proj_mat, K, capacity_points=None, align_points=4, clusters=None):
     """Fused render_cuda_keep_in_gpu + depth2cloud_cuda per pose (pr_render_cloud_batch).
+    clusters: (vert_off, cluster_verts) from mesh_cluster -- faces must then be mesh_cluster's reordered faces.
     -> (depth [P,H,W] int32, pts [cap,3] float32, offsets [P+1] int32, counts [P] int32), all on the device.
     Cloud i = pts[offsets[i] : offsets[i] + counts[i]], the points of depth2cloud in screen-tile order."""
     _require_device()
@@ -187,9 +203,14 @@ def render_cloud_batch(verts, faces, poses, width, height, proj_mat, K, capacity
     overflow = torch.zeros(1, dtype=torch.int32, device="cuda")
     ws_bytes = lib().pr_render_cloud_workspace_bytes(n_poses, verts.shape[0], faces.shape[0], width, height)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    cl_ptr = None
+    if clusters is not None:
+        off_d, cv_d = _dev(clusters[0], torch.int32), _dev(clusters[1], torch.int32)
+        cl = _lib.MeshClusters(off_d.shape[0] - 1, off_d.data_ptr(), cv_d.data_ptr())
+        cl_ptr = C.cast(C.pointer(cl), C.c_void_p)
     check(lib().pr_render_cloud_batch(verts.data_ptr(), verts.shape[0], faces.data_ptr(), faces.shape[0], poses_t.data_ptr(), 1,
                                       n_poses, width, height, proj.ctypes.data, Kc.ctypes.data, depth.data_ptr(), pts.data_ptr(),
-                                      cap, align_points, counts.data_ptr(), offsets.data_ptr(), overflow.data_ptr(),
+                                      cap, align_points, counts.data_ptr(), offsets.data_ptr(), overflow.data_ptr(), cl_ptr,
                                       ws.data_ptr(), ws_bytes, _stream()), "pr_render_cloud_batch")
     return depth, pts, offsets, counts
 

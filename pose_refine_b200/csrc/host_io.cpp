@@ -13,6 +13,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include <sstream>
 #include <fstream>
 
@@ -163,6 +164,64 @@ int pr_mesh_index(const float* tris_host, size_t n_tris, float* verts_out, int32
     }
     *n_verts = verts.size() / 3;
     if (verts_out) memcpy(verts_out, verts.data(), verts.size() * 4);
+    return PR_OK;
+}
+
+// Morton (z-order) code of a point quantised to 10 bits per axis
+static inline uint32_t spread10(uint32_t v) {
+    v &= 0x3FF;
+    v = (v | (v << 16)) & 0x030000FF;
+    v = (v | (v << 8)) & 0x0300F00F;
+    v = (v | (v << 4)) & 0x030C30C3;
+    v = (v | (v << 2)) & 0x09249249;
+    return v;
+}
+
+int pr_mesh_cluster(const float* verts, size_t n_verts, int32_t* faces, size_t n_tris, int32_t* cluster_vert_off,
+                    int32_t* cluster_verts, size_t* n_clusters) {
+    if (!verts || !faces || !cluster_vert_off || !cluster_verts || !n_clusters || n_verts == 0) return PR_ERR_INVALID_ARGUMENT;
+    const size_t kTris = 64;
+    for (size_t i = 0; i < 3 * n_tris; i++)
+        if (faces[i] < 0 || (size_t)faces[i] >= n_verts) return PR_ERR_INVALID_ARGUMENT;
+    float lo[3] = {verts[0], verts[1], verts[2]}, hi[3] = {verts[0], verts[1], verts[2]};
+    for (size_t v = 0; v < n_verts; v++)
+        for (int a = 0; a < 3; a++) {
+            const float x = verts[3 * v + a];
+            if (x < lo[a]) lo[a] = x;
+            if (x > hi[a]) hi[a] = x;
+        }
+    std::vector<std::pair<uint32_t, uint32_t>> keys(n_tris);       // (morton code of the centroid, face)
+    for (size_t t = 0; t < n_tris; t++) {
+        uint32_t code = 0;
+        for (int a = 0; a < 3; a++) {
+            const float c = (verts[3 * (size_t)faces[3 * t] + a] + verts[3 * (size_t)faces[3 * t + 1] + a] + verts[3 * (size_t)faces[3 * t + 2] + a]) / 3.f;
+            const float ext = hi[a] - lo[a];
+            float q = ext > 0.f ? (c - lo[a]) / ext * 1023.f : 0.f;
+            if (!(q >= 0.f)) q = 0.f;                              // also NaN
+            if (q > 1023.f) q = 1023.f;
+            code |= spread10((uint32_t)q) << a;
+        }
+        keys[t] = {code, (uint32_t)t};
+    }
+    std::stable_sort(keys.begin(), keys.end(), [](const std::pair<uint32_t, uint32_t>& a, const std::pair<uint32_t, uint32_t>& b) { return a.first < b.first; });
+    std::vector<int32_t> sorted(3 * n_tris);
+    for (size_t t = 0; t < n_tris; t++)
+        for (int k = 0; k < 3; k++) sorted[3 * t + k] = faces[3 * (size_t)keys[t].second + k];
+    memcpy(faces, sorted.data(), sorted.size() * sizeof(int32_t));
+    // unique vertices per cluster, in order of first use
+    const size_t nc = (n_tris + kTris - 1) / kTris;
+    std::vector<int32_t> stamp(n_verts, -1);
+    size_t n = 0;
+    for (size_t c = 0; c < nc; c++) {
+        cluster_vert_off[c] = (int32_t)n;
+        const size_t t1 = std::min(n_tris, (c + 1) * kTris);
+        for (size_t i = 3 * c * kTris; i < 3 * t1; i++) {
+            const int32_t v = faces[i];
+            if (stamp[v] != (int32_t)c) { stamp[v] = (int32_t)c; cluster_verts[n++] = v; }
+        }
+    }
+    cluster_vert_off[nc] = (int32_t)n;
+    *n_clusters = nc;
     return PR_OK;
 }
 

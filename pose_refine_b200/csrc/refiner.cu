@@ -23,6 +23,8 @@ struct pr_refiner {
     float* d_verts = nullptr;     // deduplicated mesh (pr_mesh_index): the refiner renders the indexed form
     int32_t* d_faces = nullptr;
     size_t n_verts = 0;
+    int32_t *d_cl_off = nullptr, *d_cl_verts = nullptr;
+    pr_mesh_clusters clusters = {0, nullptr, nullptr};
     float* d_poses = nullptr;
     int32_t* d_depth = nullptr;
     float* d_pts = nullptr;
@@ -54,7 +56,7 @@ int run_device(pr_refiner* r, const float* poses_dev, size_t n_hyp, pr_icp_crite
     // render + clouds in one pass over the depth batch (tile-ordered clouds; the reduction does not care about order)
     int rc = pr_render_cloud_batch(r->d_verts, r->n_verts, r->d_faces, r->n_tris, poses_dev, 1, n_hyp, r->W, r->H, r->proj, r->K,
                                    r->d_depth, r->d_pts, r->capacity_points, 4, r->d_counts, r->d_offsets, r->d_overflow,
-                                   r->ws_render, r->ws_render_bytes, s);
+                                   &r->clusters, r->ws_render, r->ws_render_bytes, s);
     if (rc != PR_OK) return rc;
     if (r->scene_kind == 0)
         return pr_icp_projective_batch(r->d_pts, r->d_offsets, r->d_counts, n_hyp, r->capacity_points, &r->sp, crit, results_dev, 0,
@@ -134,6 +136,11 @@ int pr_refiner_create(pr_refiner** out, const float* tris_host, size_t n_tris, u
     std::vector<int32_t> faces(n_tris * 3);
     rc = pr_mesh_index(tris_host, n_tris, verts.data(), faces.data(), &r->n_verts);
     if (rc != PR_OK) { delete r; return rc; }
+    // Morton-ordered faces + clusters: the rasteriser bins 64-triangle clusters instead of triangles
+    std::vector<int32_t> cl_off((n_tris + 63) / 64 + 1), cl_verts(3 * n_tris);
+    size_t n_clusters = 0;
+    rc = pr_mesh_cluster(verts.data(), r->n_verts, faces.data(), n_tris, cl_off.data(), cl_verts.data(), &n_clusters);
+    if (rc != PR_OK) { delete r; return rc; }
     r->ws_render_bytes = pr_render_cloud_workspace_bytes(max_hyp, r->n_verts, n_tris, width, height);
     r->ws_cloud_bytes = pr_depth2cloud_workspace_bytes(max_hyp, width, height);
     r->ws_icp_bytes = pr_icp_workspace_bytes(max_hyp, r->capacity_points, 3 * n_px + 16);   // projective: n_px; kd-tree: <= n_px points + 2 * (2 n_px + 1) nodes... bounded by 3 n_px for leaf >= 2
@@ -142,6 +149,8 @@ int pr_refiner_create(pr_refiner** out, const float* tris_host, size_t n_tris, u
     alloc((void**)&r->d_tris, n_tris * 36);
     alloc((void**)&r->d_verts, r->n_verts * 12);
     alloc((void**)&r->d_faces, n_tris * 12);
+    alloc((void**)&r->d_cl_off, (n_clusters + 1) * 4);
+    alloc((void**)&r->d_cl_verts, (size_t)cl_off[n_clusters] * 4);
     alloc((void**)&r->d_poses, max_hyp * 64);
     alloc((void**)&r->d_depth, max_hyp * n_px * 4);
     alloc((void**)&r->d_pts, r->capacity_points * 12 + 64);
@@ -156,6 +165,9 @@ int pr_refiner_create(pr_refiner** out, const float* tris_host, size_t n_tris, u
     if (e == cudaSuccess) e = cudaMemcpy(r->d_tris, tris_host, n_tris * 36, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(r->d_verts, verts.data(), r->n_verts * 12, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(r->d_faces, faces.data(), n_tris * 12, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_cl_off, cl_off.data(), (n_clusters + 1) * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_cl_verts, cl_verts.data(), (size_t)cl_off[n_clusters] * 4, cudaMemcpyHostToDevice);
+    r->clusters.n_clusters = n_clusters; r->clusters.vert_off_dev = r->d_cl_off; r->clusters.verts_dev = r->d_cl_verts;
     if (e == cudaSuccess) e = cudaMemset(r->d_overflow, 0, 256);
     if (e != cudaSuccess) { pr_refiner_destroy(r); return (int)e; }
     *out = r;
@@ -165,7 +177,7 @@ int pr_refiner_create(pr_refiner** out, const float* tris_host, size_t n_tris, u
 void pr_refiner_destroy(pr_refiner* r) {
     if (!r) return;
     free_scene(r);
-    cudaFree(r->d_tris); cudaFree(r->d_verts); cudaFree(r->d_faces); cudaFree(r->d_poses); cudaFree(r->d_depth); cudaFree(r->d_pts);
+    cudaFree(r->d_tris); cudaFree(r->d_verts); cudaFree(r->d_faces); cudaFree(r->d_cl_off); cudaFree(r->d_cl_verts); cudaFree(r->d_poses); cudaFree(r->d_depth); cudaFree(r->d_pts);
     cudaFree(r->d_counts); cudaFree(r->d_offsets); cudaFree(r->d_overflow); cudaFree(r->d_results);
     cudaFree(r->ws_render); cudaFree(r->ws_cloud); cudaFree(r->ws_icp);
     if (r->h_overflow) cudaFreeHost(r->h_overflow);

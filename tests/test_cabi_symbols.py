@@ -122,3 +122,23 @@ def test_product_does_not_reference_the_oracle():
                     text = open(os.path.join(dp, fn), errors="ignore").read()
                     assert "liboracle" not in text and "libpose_refine_ref" not in text and "from oracle" not in text \
                         and "import oracle" not in text, os.path.join(dp, fn)
+
+
+def test_mesh_cluster_host(golden):
+    """pr_mesh_cluster: a permutation of the faces in Morton order, clusters of 64, each with the list of its unique
+    vertices; nearby faces end up in the same cluster (the bounding boxes of clusters are small)."""
+    from pose_refine_b200 import api, workloads as wl
+    import os
+    mesh = wl.load_mesh_npz(os.path.join(os.path.dirname(__file__), "golden", "obj_06_mesh.npz"))
+    verts, faces = api.mesh_index(mesh)
+    cf, off, cv = api.mesh_cluster(verts, faces)
+    assert cf.shape == faces.shape and len(off) == (len(faces) + 63) // 64 + 1 and off[0] == 0 and off[-1] == len(cv)
+    assert sorted(map(tuple, cf.tolist())) == sorted(map(tuple, faces.tolist()))
+    ext = []
+    for c in range(len(off) - 1):
+        ids = cv[off[c]: off[c + 1]]
+        assert set(cf[64 * c: 64 * c + 64].reshape(-1).tolist()) == set(ids.tolist()) and len(set(ids.tolist())) == len(ids)
+        p = verts[ids]
+        ext.append((p.max(0) - p.min(0)).max())
+    full = (verts.max(0) - verts.min(0)).max()
+    assert np.median(ext) < 0.2 * full                      # clusters are spatially compact

@@ -127,8 +127,14 @@ def test_render_cloud_fused_matches_render_then_depth2cloud(api, port, mesh, gol
     verts, faces = api.mesh_index(mesh)
     poses = arrays["hyp8"].copy()
     poses[5, 2, 3] = -500.0                                   # object behind the camera: empty depth, empty cloud
-    for (W, H, proj, Kc) in [(640, 480, arrays["proj"], K), (161, 121, arrays["proj_small"], arrays["K_small"])]:
-        depth, pts, offsets, counts = api.render_cloud_batch(verts, faces, poses, W, H, proj, Kc)
+    cfaces, cl_off, cl_verts = api.mesh_cluster(verts, faces)
+    for (W, H, proj, Kc, clustered) in [(640, 480, arrays["proj"], K, False), (640, 480, arrays["proj"], K, True),
+                                        (161, 121, arrays["proj_small"], arrays["K_small"], False),
+                                        (161, 121, arrays["proj_small"], arrays["K_small"], True)]:
+        if clustered:     # 64-triangle clusters binned instead of triangles: same depth, same clouds
+            depth, pts, offsets, counts = api.render_cloud_batch(verts, cfaces, poses, W, H, proj, Kc, clusters=(cl_off, cl_verts))
+        else:
+            depth, pts, offsets, counts = api.render_cloud_batch(verts, faces, poses, W, H, proj, Kc)
         depth, pts, offsets, counts = depth.cpu().numpy(), pts.cpu().numpy(), offsets.cpu().numpy(), counts.cpu().numpy()
         want_depth = port.render(mesh, poses, W, H, proj)
         assert np.array_equal(depth, want_depth)
@@ -150,6 +156,30 @@ def test_render_cloud_fused_matches_render_then_depth2cloud(api, port, mesh, gol
                 x0 = xs[sel & (ys == y0)].min()
                 z = np.float32(want_depth[i][y0, x0]) / np.float32(1000.0)
                 assert got[0, 2] == z
+
+
+def test_render_clustered_edge_cases(api, port, golden):
+    """Cluster binning with meshes that stress it: big triangles (every cluster spans many tiles), a sphere partly behind
+    the camera (non-finite / negative-z vertices inside clusters), a mesh smaller than one cluster."""
+    arrays, _ = golden
+    K = arrays["K"]
+    rng = np.random.RandomState(7)
+    big = (rng.uniform(-300, 300, size=(200, 9))).astype(np.float32)
+    big[:, 2::3] = rng.uniform(-20, 20, size=(200, 3))
+    sphere = wl.uv_sphere(50.0, 40, 37)
+    tiny = sphere[:5].copy()
+    poses = wl.hypotheses(3, seed=3)
+    sposes = wl.shoemake_poses(3, seed=5)
+    sposes[2, 2, 3] = 30.0                                   # camera inside the sphere's depth range
+    for tris, ps in [(big, poses), (sphere, sposes), (tiny, sposes)]:
+        v, f = api.mesh_index(tris)
+        cf, off, cv = api.mesh_cluster(v, f)
+        assert sorted(map(tuple, cf.tolist())) == sorted(map(tuple, f.tolist()))          # a permutation of the faces
+        assert off[0] == 0 and len(off) == (len(f) + 63) // 64 + 1
+        for c in range(len(off) - 1):                                                      # vertex lists cover their faces
+            assert set(cf[64 * c: 64 * c + 64].reshape(-1).tolist()) == set(cv[off[c]: off[c + 1]].tolist())
+        depth, _, _, _ = api.render_cloud_batch(v, cf, ps, 640, 480, arrays["proj"], K, clusters=(off, cv))
+        assert np.array_equal(depth.cpu().numpy(), port.render(tris, ps, 640, 480, arrays["proj"]))
 
 
 def test_render_big_triangles_overflowing_bins(api, port, golden):
