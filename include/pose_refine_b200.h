@@ -200,6 +200,17 @@ int pr_scene_nn_build_host(const void* depth_host, int depth_is_int32, uint32_t 
                            const float K[9], int max_leaf, float* pcd_host, float* normal_host, size_t capacity_points,
                            pr_node_kdtree* nodes_host, size_t capacity_nodes, size_t* n_points, size_t* n_nodes);
 
+/* The same build on the DEVICE (no upstream counterpart: init_Scene_nn_cuda builds on the host and uploads,       */
+/* pcd_scene.cu:3-20; its README names a GPU build as future work).  depth_dev: uint16 or int32 image in device     */
+/* memory.  Writes the leaf-ordered points / normals (capacity_points * 3 floats each) and the nodes                 */
+/* (capacity_nodes; 2 * n_points + 1 always suffices) to DEVICE buffers -- bit-identical to pr_scene_nn_build_host.   */
+/* Synchronous (one small device -> host read per tree level).  PR_ERR_CAPACITY when a buffer is too small            */
+/* (*n_points / *n_nodes then hold the sizes needed so far).                                                          */
+size_t pr_scene_nn_build_workspace_bytes(uint32_t width, uint32_t height);
+int pr_scene_nn_build(const void* depth_dev, int depth_is_int32, uint32_t width, uint32_t height, const float K[9], int max_leaf,
+                      float* pcd_dev, float* normal_dev, size_t capacity_points, pr_node_kdtree* nodes_dev, size_t capacity_nodes,
+                      size_t* n_points, size_t* n_nodes, void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------- */
 /* ICP: replaces ICP_Point2Plane_cuda<Scene> (icp.cu:156-223), thrust__pcd2Ab (icp.h:128-209),   */
 /* Scene_*::query (depth_scene.h:30-48, pcd_scene.h:61-136), transform_pcd_cuda (icp.cu:142-153) */

@@ -57,6 +57,8 @@ PROTOTYPES = {
     "pr_depth2cloud_fill": (_i, [_vp, _i, _sz, _u32, _u32, _vp, _u32, _u32, _u32, _vp, _vp, _sz, _vp, _sz, _vp]),
     "pr_scene_projective_init": (_i, [_vp, _i, _u32, _u32, _vp, _vp, _vp, _vp]),
     "pr_scene_nn_build_host": (_i, [_vp, _i, _u32, _u32, _vp, _i, _vp, _vp, _sz, _vp, _sz, C.POINTER(_sz), C.POINTER(_sz)]),
+    "pr_scene_nn_build_workspace_bytes": (_sz, [_u32, _u32]),
+    "pr_scene_nn_build": (_i, [_vp, _i, _u32, _u32, _vp, _i, _vp, _vp, _sz, _vp, _sz, C.POINTER(_sz), C.POINTER(_sz), _vp, _sz, _vp]),
     "pr_icp_workspace_bytes": (_sz, [_sz, _sz, _sz]),
     "pr_icp_projective_batch": (_i, [_vp, _vp, _vp, _sz, _sz, C.POINTER(SceneProjective), Criteria, _vp, _i, _vp, _sz, _vp]),
     "pr_icp_nn_batch": (_i, [_vp, _vp, _vp, _sz, _sz, C.POINTER(SceneNN), Criteria, _vp, _i, _vp, _sz, _vp]),

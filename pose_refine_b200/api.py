@@ -320,7 +320,31 @@ class SceneNN:
         self.nodes_host = None
 
     def init_cuda(self, scene_depth, K, max_leaf=10):
-        """init_Scene_nn_cuda (pcd_scene.cu:3-20): kd-tree built on the host, uploaded."""
+        """init_Scene_nn_cuda (pcd_scene.cu:3-20) with the kd-tree built on the DEVICE (pr_scene_nn_build): the same
+        arrays the host build produces, bit for bit."""
+        _require_device()
+        d = scene_depth if isinstance(scene_depth, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(scene_depth))
+        assert d.dtype in (torch.int32, torch.uint16), "CV_16U or CV_32S (pcd_scene.cpp:6-7)"
+        d = d.cuda().contiguous()
+        H, W = d.shape
+        K = _f32c(K).reshape(9)
+        cap = H * W
+        self.pcd = torch.zeros((cap, 3), dtype=torch.float32, device="cuda")
+        self.normal = torch.zeros((cap, 3), dtype=torch.float32, device="cuda")
+        nodes = torch.zeros((2 * cap + 1) * 52, dtype=torch.uint8, device="cuda")
+        ws_bytes = lib().pr_scene_nn_build_workspace_bytes(W, H)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+        n_pts, n_nodes = C.c_size_t(), C.c_size_t()
+        check(lib().pr_scene_nn_build(d.data_ptr(), int(d.dtype == torch.int32), W, H, K.ctypes.data, max_leaf, self.pcd.data_ptr(),
+                                      self.normal.data_ptr(), cap, nodes.data_ptr(), 2 * cap + 1, C.byref(n_pts), C.byref(n_nodes),
+                                      ws.data_ptr(), ws_bytes, _stream()), "pr_scene_nn_build")
+        self.pcd, self.normal = self.pcd[: n_pts.value].contiguous(), self.normal[: n_pts.value].contiguous()
+        self.nodes = nodes[: max(n_nodes.value, 1) * 52].contiguous()
+        self.nodes_host = np.ascontiguousarray(self.nodes[: n_nodes.value * 52].cpu().numpy()).view(NODE_DTYPE)
+        return self
+
+    def init_host_build(self, scene_depth, K, max_leaf=10):
+        """init_Scene_nn_cuda (pcd_scene.cu:3-20) as upstream does it: kd-tree built on the host, uploaded."""
         _require_device()
         d = np.ascontiguousarray(scene_depth.cpu().numpy() if isinstance(scene_depth, torch.Tensor) else scene_depth)
         assert d.dtype in (np.int32, np.uint16), "CV_16U or CV_32S (pcd_scene.cpp:6-7)"

@@ -208,19 +208,23 @@ int pr_refiner_set_scene_nn(pr_refiner* r, const void* depth_host, int depth_is_
     if (!r || !depth_host) return PR_ERR_INVALID_ARGUMENT;
     free_scene(r);
     const size_t n_px = (size_t)r->W * r->H;
-    std::vector<float> pcd(n_px * 3), nrm(n_px * 3);
-    std::vector<pr_node_kdtree> nodes(2 * n_px + 1);
+    const size_t px_bytes = depth_is_int32 ? 4 : 2;
+    // upload the image and build everything on the device (pr_scene_nn_build): points, normals, kd-tree
+    void *d_depth = nullptr, *d_ws = nullptr;
+    const size_t ws_bytes = pr_scene_nn_build_workspace_bytes(r->W, r->H);
     size_t n_pts = 0, n_nodes = 0;
-    int rc = pr_scene_nn_build_host(depth_host, depth_is_int32, r->W, r->H, r->K, 10, pcd.data(), nrm.data(), n_px,
-                                    nodes.data(), nodes.size(), &n_pts, &n_nodes);
-    if (rc != PR_OK) return rc;
-    cudaError_t e = cudaMalloc((void**)&r->d_scene_pcd, n_pts * 12 + 256);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_scene_nrm, n_pts * 12 + 256);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_nodes, n_nodes * sizeof(pr_node_kdtree) + 256);
-    if (e == cudaSuccess) e = cudaMemcpy(r->d_scene_pcd, pcd.data(), n_pts * 12, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(r->d_scene_nrm, nrm.data(), n_pts * 12, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(r->d_nodes, nodes.data(), n_nodes * sizeof(pr_node_kdtree), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { free_scene(r); return (int)e; }
+    cudaError_t e = cudaMalloc(&d_depth, n_px * px_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_ws, ws_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_scene_pcd, n_px * 12 + 256);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_scene_nrm, n_px * 12 + 256);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_nodes, (2 * n_px + 1) * sizeof(pr_node_kdtree));
+    if (e == cudaSuccess) e = cudaMemcpy(d_depth, depth_host, n_px * px_bytes, cudaMemcpyHostToDevice);
+    int rc = (e == cudaSuccess) ? PR_OK : (int)e;
+    if (rc == PR_OK)
+        rc = pr_scene_nn_build(d_depth, depth_is_int32, r->W, r->H, r->K, 10, r->d_scene_pcd, r->d_scene_nrm, n_px, r->d_nodes,
+                               2 * n_px + 1, &n_pts, &n_nodes, d_ws, ws_bytes, nullptr);
+    cudaFree(d_depth); cudaFree(d_ws);
+    if (rc != PR_OK) { free_scene(r); return rc; }
     r->sn.max_dist_diff = 0.1f;   // Scene_nn has no setter upstream (pcd_scene.h:49)
     r->sn.pcd_dev = r->d_scene_pcd; r->sn.normal_dev = r->d_scene_nrm; r->sn.nodes_dev = r->d_nodes;
     r->sn.n_points = n_pts; r->sn.n_nodes = n_nodes;

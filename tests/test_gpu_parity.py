@@ -287,6 +287,21 @@ def test_scene_nn_build_bit_exact(api, port, fixture_scene, golden):
     wp, wn, wnodes = port.scene_nn(comp, K).arrays()
     assert np.array_equal(s.pcd.cpu().numpy(), wp) and np.array_equal(s.normal.cpu().numpy(), wn)
     assert s.nodes_host.tobytes() == wnodes.tobytes()
+    # the host build (upstream's way) gives the same bytes
+    h = api.SceneNN().init_host_build(comp, K)
+    assert np.array_equal(h.pcd.cpu().numpy(), wp) and h.nodes_host.tobytes() == wnodes.tobytes()
+    # fronto-parallel patch: every column shares x and every row shares y exactly, so the cut is hit by many points
+    # (the alternating tie rule, pcd_scene.cpp:121-127); plus an empty image and one with fewer points than a leaf
+    flat = np.zeros((480, 640), np.int32); flat[100:180, 200:330] = 700
+    few = np.zeros((480, 640), np.int32); few[240, 300:307] = 650
+    s = api.SceneNN().init_cuda(np.zeros((480, 640), np.int32), K)      # upstream asserts on an empty cloud (pcd_scene.cpp:47)
+    assert s.pcd.shape[0] == 0 and len(s.nodes_host) == 0
+    for img in (flat, few, flat.astype(np.uint16)):
+        s = api.SceneNN().init_cuda(img, K)
+        wp, wn, wnodes = port.scene_nn(img, K).arrays()
+        assert s.pcd.shape[0] == wp.shape[0] and len(s.nodes_host) == len(wnodes)
+        assert np.array_equal(s.pcd.cpu().numpy(), wp) and np.array_equal(s.normal.cpu().numpy(), wn)
+        assert s.nodes_host.tobytes() == wnodes.tobytes()
 
 
 # ---------------------------------------------------------------------------------------------
