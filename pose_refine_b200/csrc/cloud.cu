@@ -197,16 +197,17 @@ tile_scan_kernel(const uint32_t* __restrict__ tile_valid, uint32_t* __restrict__
 // non-empty tiles, so only the ~10 % of tiles the object covers are read again (the segment-based pass above reads
 // every pixel of every image twice, and a grid with one CTA per tile spends its time launching 70k empty CTAs).  Points of an image are ordered tile by
 // tile (row-major tiles, row-major pixels inside a tile) -- deterministic, but NOT depth2cloud_cuda's row-major
-// order; the coordinates themselves are the same values.  Tile = 64 x 32 pixels = kSegPx, 8 pixels per thread.
+// order; the coordinates themselves are the same values.  A tile is 64 pixels wide and a multiple of 32 rows high; a
+// band of 32 rows = kSegPx pixels is handled per step, 8 pixels per thread.
 constexpr int kFillCtas = 16;
 __global__ void __launch_bounds__(kSegThreads)
 cloud_fill_tiles_kernel(const int32_t* __restrict__ depth, uint32_t width, uint32_t height, int tiles_x, uint32_t n_tiles,
                         const unsigned* __restrict__ tile_list, const unsigned* __restrict__ n_list,
                         const unsigned* __restrict__ tile_off,
                         const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts, Intrinsics K,
-                        float* __restrict__ out, size_t capacity) {
+                        float* __restrict__ out, size_t capacity, int tile_h) {
     __shared__ unsigned s_warp[kSegThreads / 32];
-    __shared__ float s_fx[64], s_fy[32];                          // (u - cx) / fx per tile column, (v - cy) / fy per tile row
+    __shared__ float s_fx[64], s_fy[128];                         // (u - cx) / fx per tile column, (v - cy) / fy per tile row
     const uint32_t image = blockIdx.y;
     if (counts[image] == 0) return;                               // empty, or the cloud did not fit (overflow)
     const uint32_t n_here = n_list[image];
@@ -217,9 +218,11 @@ cloud_fill_tiles_kernel(const int32_t* __restrict__ depth, uint32_t width, uint3
     // the two pixel-only factors of icp.cu:250-251, one IEEE division per thread instead of two per point
     __syncthreads();
     if (threadIdx.x < 64) s_fx[threadIdx.x] = divf(subf((float)(tx * 64 + threadIdx.x), K.cx), K.fx);
-    else if (threadIdx.x < 96) s_fy[threadIdx.x - 64] = divf(subf((float)(ty * 32 + threadIdx.x - 64), K.cy), K.fy);
+    else if ((int)threadIdx.x < 64 + tile_h) s_fy[threadIdx.x - 64] = divf(subf((float)(ty * tile_h + threadIdx.x - 64), K.cy), K.fy);
     __syncthreads();
-    const uint32_t v = ty * 32 + (threadIdx.x >> 3);              // 8 threads per tile row
+    unsigned done = 0;                                            // points of this tile written by earlier 32-row bands
+   for (int band = 0; band < tile_h; band += 32) {
+    const uint32_t v = ty * tile_h + band + (threadIdx.x >> 3);   // 8 threads per tile row, 32 rows per band
     const uint32_t u0 = tx * 64 + (threadIdx.x & 7) * 8;
     const int32_t* img = depth + (size_t)image * width * height;
     int d[kPxPerThread];
@@ -241,7 +244,8 @@ cloud_fill_tiles_kernel(const int32_t* __restrict__ depth, uint32_t width, uint3
     }
     unsigned total;
     const unsigned excl = block_excl_scan(c, s_warp, &total);
-    size_t dst = (size_t)offsets[image] + tile_off[t_idx] + excl;
+    size_t dst = (size_t)offsets[image] + tile_off[t_idx] + done + excl;
+    done += total;
 #pragma unroll
     for (int k = 0; k < kPxPerThread; k++) {
         if (d[k] > 0) {
@@ -249,12 +253,13 @@ cloud_fill_tiles_kernel(const int32_t* __restrict__ depth, uint32_t width, uint3
                 // icp.cu:249-251
                 const float z = divf((float)d[k], 1000.0f);
                 const float x = mulf(s_fx[(threadIdx.x & 7) * 8 + k], z);
-                const float y = mulf(s_fy[threadIdx.x >> 3], z);
+                const float y = mulf(s_fy[band + (threadIdx.x >> 3)], z);
                 out[3 * dst + 0] = x; out[3 * dst + 1] = y; out[3 * dst + 2] = z;
             }
             dst++;
         }
     }
+   }
   }
 }
 
@@ -264,7 +269,7 @@ int cloud_from_tiles(const int32_t* depth_dev, size_t n_images, uint32_t width, 
                      int tile_w, int tile_h, int tiles_x, int tiles_y, const unsigned* tile_valid, unsigned* tile_off,
                      uint32_t* counts_dev, uint32_t* offsets_dev, uint32_t* overflow_dev, size_t capacity_points,
                      uint32_t align_points, float* out_pts_dev, cudaStream_t stream) {
-    if (tile_w != 64 || tile_h != 32) return PR_ERR_UNSUPPORTED;       // the fill kernel's thread -> pixel map
+    if (tile_w != 64 || tile_h % 32 != 0 || tile_h > 128) return PR_ERR_UNSUPPORTED;       // the fill kernel's thread -> pixel map
     const uint32_t n_tiles = (uint32_t)(tiles_x * tiles_y);
     // scratch behind the offsets: list of non-empty tiles per image, then the list lengths (see cloud_tiles_scratch_words)
     unsigned* tile_list = tile_off + n_images * (size_t)n_tiles;
@@ -276,7 +281,7 @@ int cloud_from_tiles(const int32_t* depth_dev, size_t n_images, uint32_t width, 
     const Intrinsics Ki = {K[0], K[4], K[2], K[5]};
     cloud_fill_tiles_kernel<<<dim3(kFillCtas, (unsigned)n_images), kSegThreads, 0, stream>>>(
         depth_dev, width, height, tiles_x, n_tiles, tile_list, n_list, tile_off, offsets_dev, counts_dev, Ki, out_pts_dev,
-        capacity_points ? capacity_points : ~(size_t)0);
+        capacity_points ? capacity_points : ~(size_t)0, tile_h);
     count_launch(3);
     PR_LAUNCH_CHECK();
     return PR_OK;

@@ -180,7 +180,10 @@ static inline uint32_t spread10(uint32_t v) {
 int pr_mesh_cluster(const float* verts, size_t n_verts, int32_t* faces, size_t n_tris, int32_t* cluster_vert_off,
                     int32_t* cluster_verts, size_t* n_clusters) {
     if (!verts || !faces || !cluster_vert_off || !cluster_verts || !n_clusters || n_verts == 0) return PR_ERR_INVALID_ARGUMENT;
-    const size_t kTris = 64;
+#ifndef PR_CLUSTER_TRIS
+#define PR_CLUSTER_TRIS 64
+#endif
+    const size_t kTris = PR_CLUSTER_TRIS;
     for (size_t i = 0; i < 3 * n_tris; i++)
         if (faces[i] < 0 || (size_t)faces[i] >= n_verts) return PR_ERR_INVALID_ARGUMENT;
     float lo[3] = {verts[0], verts[1], verts[2]}, hi[3] = {verts[0], verts[1], verts[2]};

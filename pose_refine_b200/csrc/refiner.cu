@@ -137,7 +137,7 @@ int pr_refiner_create(pr_refiner** out, const float* tris_host, size_t n_tris, u
     rc = pr_mesh_index(tris_host, n_tris, verts.data(), faces.data(), &r->n_verts);
     if (rc != PR_OK) { delete r; return rc; }
     // Morton-ordered faces + clusters: the rasteriser bins 64-triangle clusters instead of triangles
-    std::vector<int32_t> cl_off((n_tris + 63) / 64 + 1), cl_verts(3 * n_tris);
+    std::vector<int32_t> cl_off(n_tris + 2), cl_verts(3 * n_tris);
     size_t n_clusters = 0;
     rc = pr_mesh_cluster(verts.data(), r->n_verts, faces.data(), n_tris, cl_off.data(), cl_verts.data(), &n_clusters);
     if (rc != PR_OK) { delete r; return rc; }

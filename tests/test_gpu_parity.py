@@ -147,9 +147,9 @@ def test_render_cloud_fused_matches_render_then_depth2cloud(api, port, mesh, gol
             ks, kg = np.lexsort((want[:, 0], want[:, 1])), np.lexsort((got[:, 0], got[:, 1]))
             assert np.array_equal(want[ks], got[kg]), f"pose {i}: fused cloud differs from depth2cloud of the same depth"
             if W == 640 and counts[i]:
-                # tile order: the first point lies in the first non-empty 64x32 tile (row-major tiles)
+                # tile order: the first point lies in the first non-empty 64x64 tile (row-major tiles)
                 ys, xs = np.nonzero(want_depth[i])
-                tiles = (ys // 32) * 10 + xs // 64
+                tiles = (ys // 64) * 10 + xs // 64
                 first = tiles.min()
                 sel = tiles == first
                 y0, x0 = ys[sel].min(), None
