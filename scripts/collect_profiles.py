@@ -26,7 +26,7 @@ with open(os.path.join(P, f"{R}_launches_bench.md"), "w") as f:
             "`ncu --metrics gpu__time_duration.sum --clock-control none -s 25 -c 40` (cold-cache, serialised: compare shares).\n\n"
             "| kernel | launches | total us | mean us | share |\n|---|---:|---:|---:|---:|\n")
     for k, a in agg.items(): f.write(f"| {k} | {a[0]} | {a[1]:.1f} | {a[1]/a[0]:.1f} | {a[1]/tot*100:.1f}% |\n")
-    f.write(f"\nTotal {tot:.1f} us over {n} launches.  One refiner step = vertex, bin count, bin scan, bin fill, raster tile, tile scan, "
+    f.write(f"\nTotal {tot:.1f} us over {n} launches.  One refiner step = vertex, cluster span, bin scan, cluster fill, raster tile, tile scan, "
             "cloud offsets, cloud fill (tiles), scene pack, ICP plan, ICP persistent (+ 1 memset); the capture window also holds the "
             "per-stage timing calls of bench.py, which go through the public depth2cloud entry points (cloud_count / cloud_scan / cloud_fill).\n")
 
