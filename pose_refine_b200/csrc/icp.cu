@@ -701,7 +701,16 @@ icp_pass_kernel(const float* __restrict__ pts, const uint32_t* __restrict__ offs
 constexpr int kPThreads = PR_PTHREADS;         // threads per CTA of the persistent kernel
 constexpr int kPWarps = kPThreads / 32;
 constexpr int kWTile = PR_WTILE;               // points per warp tile of the projective driver (12 KB at 1024)
-constexpr int kWTileNn = 512;                  // nearest-neighbour scenes: small tiles, so that several CTAs fit an SM
+// nearest-neighbour driver (measured, 512 hypotheses against a 99k-point tree): tile 512 / 2 CTAs per SM 181 ms,
+// tile 256 / 2 CTAs 125 ms, tile 128 / 4 CTAs 102 ms -- the tree walk lives in L1, so every KB of shared memory
+// given back to L1 and every extra resident warp counts, even at 64 registers per thread
+#ifndef PR_NN_TILE
+#define PR_NN_TILE 128
+#endif
+#ifndef PR_NN_MINB
+#define PR_NN_MINB 4
+#endif
+constexpr int kWTileNn = PR_NN_TILE;           // nearest-neighbour scenes: small tiles, so that several CTAs fit an SM
 constexpr int kWStages = 2;
 constexpr uint32_t kPersistChunk = PR_CHUNK;   // points per work item of a large batch (see persist_chunk_points)
 constexpr int kIlp = PR_ILP;                   // points per lane per group (gathers in flight per lane)
@@ -1057,8 +1066,8 @@ __device__ __forceinline__ bool stage_tile(const float* src, unsigned n, uintptr
     return tma;
 }
 
-// projective: one CTA of register-rich warps per SM; nearest neighbour: two CTAs (the tree walk hides latency with warps)
-template <class SceneT> struct MinBlocksOf { static constexpr int kValue = std::is_same<SceneT, PackedScene>::value ? PR_MINB : 2; };
+// projective: one CTA of register-rich warps per SM; nearest neighbour: four CTAs (the tree walk hides latency with warps)
+template <class SceneT> struct MinBlocksOf { static constexpr int kValue = std::is_same<SceneT, PackedScene>::value ? PR_MINB : PR_NN_MINB; };
 template <class SceneT>
 __global__ void __launch_bounds__(kPThreads, MinBlocksOf<SceneT>::kValue)
 icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, const uint4* __restrict__ chunk_info, IcpCtl* ctl,
@@ -1283,8 +1292,14 @@ int persistent_grid(int* grid_out) {
 // release fence, ticket: 4096 beats 2048 by 10 % on 512 hypotheses), but a pass must still consist of a
 // few items per resident warp or the warps run into the pass-to-pass dependency of their hypotheses
 // (8192: +30 %), and a small batch needs enough items to occupy the machine at all.
+#ifndef PR_NN_CHUNK
+#define PR_NN_CHUNK 1024
+#endif
+// nearest-neighbour scenes: a point costs ~50x more (tree walk), so the per-item cost is irrelevant and small items
+// balance better
+template <class PScene>
 inline uint32_t persist_chunk_points(size_t n_hyp, size_t capacity_points) {
-    uint32_t chunk = kPersistChunk;
+    uint32_t chunk = std::is_same<PScene, PackedScene>::value ? kPersistChunk : (uint32_t)PR_NN_CHUNK;
     while (chunk > 512 && capacity_points / chunk + n_hyp < (size_t)kNumSMs * kPWarps * 2) chunk >>= 1;
     return chunk;
 }
@@ -1311,7 +1326,7 @@ int run_icp(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_
         PR_LAUNCH_CHECK();
         return PR_OK;
     }
-    const uint32_t chunk_pts = persist_chunk_points(n_hyp, capacity_points);
+    const uint32_t chunk_pts = persist_chunk_points<PScene>(n_hyp, capacity_points);
     const size_t max_items = (capacity_points / chunk_pts + n_hyp + 1) * (size_t)(crit.max_iteration + 1);
     if (max_items > 0x7FFFFFFFull) return PR_ERR_INVALID_ARGUMENT;
     icp_plan_kernel<<<1, kIcpThreads, 0, stream>>>(counts_dev, (uint32_t)n_hyp, chunk_pts, ws.state, ws.chunk_hyp,
