@@ -208,6 +208,7 @@ cloud_fill_tiles_kernel(const int32_t* __restrict__ depth, uint32_t width, uint3
                         float* __restrict__ out, size_t capacity, int tile_h) {
     __shared__ unsigned s_warp[kSegThreads / 32];
     __shared__ float s_fx[64], s_fy[128];                         // (u - cx) / fx per tile column, (v - cy) / fy per tile row
+    __shared__ float s_pts[kSegThreads / 32][32 * kPxPerThread * 3];   // per warp: its compacted points of one band
     const uint32_t image = blockIdx.y;
     if (counts[image] == 0) return;                               // empty, or the cloud did not fit (overflow)
     const uint32_t n_here = n_list[image];
@@ -244,21 +245,35 @@ cloud_fill_tiles_kernel(const int32_t* __restrict__ depth, uint32_t width, uint3
     }
     unsigned total;
     const unsigned excl = block_excl_scan(c, s_warp, &total);
-    size_t dst = (size_t)offsets[image] + tile_off[t_idx] + done + excl;
-    done += total;
+    // The points of a warp (4 tile rows) are consecutive in the output.  Each lane parks its points in the warp's
+    // shared-memory block at its rank, then the warp copies the block with lane-consecutive stores (a lane writing its
+    // own points directly scatters 4-byte stores over 3 KB per instruction).
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned wincl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, wincl, o); if (lane >= (unsigned)o) wincl += t; }
+    const unsigned wtotal = __shfl_sync(0xffffffffu, wincl, 31);
+    unsigned slot = wincl - c;                                    // rank inside the warp
+    const unsigned wfirst = __shfl_sync(0xffffffffu, excl, 0);    // rank of the warp's first point inside the band
+    float* sp = s_pts[warp];
 #pragma unroll
     for (int k = 0; k < kPxPerThread; k++) {
         if (d[k] > 0) {
-            if (dst < capacity) {
-                // icp.cu:249-251
-                const float z = divf((float)d[k], 1000.0f);
-                const float x = mulf(s_fx[(threadIdx.x & 7) * 8 + k], z);
-                const float y = mulf(s_fy[band + (threadIdx.x >> 3)], z);
-                out[3 * dst + 0] = x; out[3 * dst + 1] = y; out[3 * dst + 2] = z;
-            }
-            dst++;
+            // icp.cu:249-251
+            const float z = divf((float)d[k], 1000.0f);
+            sp[3 * slot + 0] = mulf(s_fx[(threadIdx.x & 7) * 8 + k], z);
+            sp[3 * slot + 1] = mulf(s_fy[band + (threadIdx.x >> 3)], z);
+            sp[3 * slot + 2] = z;
+            slot++;
         }
     }
+    __syncwarp();
+    const size_t wdst = (size_t)offsets[image] + tile_off[t_idx] + done + wfirst;      // first output point of this warp
+    const size_t room = (wdst < capacity) ? capacity - wdst : 0;
+    const unsigned n_out = (unsigned)min((size_t)wtotal, room) * 3;
+    for (unsigned i = lane; i < n_out; i += 32) out[3 * wdst + i] = sp[i];
+    __syncwarp();
+    done += total;
    }
   }
 }
