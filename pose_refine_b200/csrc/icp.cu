@@ -402,31 +402,10 @@ __device__ __forceinline__ void accumulate_pair(AccP& a, f2_t px, f2_t py, f2_t 
     a.s[27] = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, a.s[27])));
 }
 
-struct Acc1 { float v[32]; };     // scalar accumulation: one FFMA per sum (first generation)
-__device__ __forceinline__ void acc_zero(Acc1& a) {
-#pragma unroll
-    for (int i = 0; i < 32; i++) a.v[i] = 0.f;
-}
 __device__ __forceinline__ void acc_zero(Acc2& a) { zero_acc2(a); }
-__device__ __forceinline__ void acc_add(Acc1& a, float px, float py, float pz, const Corr& c) { accumulate(a.v, px, py, pz, c); }
 __device__ __forceinline__ void acc_add(Acc2& a, float px, float py, float pz, const Corr& c) { accumulate2(a, px, py, pz, c); }
-__device__ __forceinline__ void acc_unpack(const Acc1& a, float (&v)[32]) {
-#pragma unroll
-    for (int i = 0; i < 32; i++) v[i] = a.v[i];
-}
 __device__ __forceinline__ void acc_unpack(const Acc2& a, float (&v)[32]) { unpack_acc2(a, v); }
-#ifndef PR_FFMA2
-#define PR_FFMA2 1
-#endif
-// PR_PAIR: the two-points-per-instruction path (AccP) for the packed projective scene in the persistent driver
-#ifndef PR_PAIR
-#define PR_PAIR 1
-#endif
-#if PR_FFMA2
-typedef Acc2 AccT;
-#else
-typedef Acc1 AccT;
-#endif
+typedef Acc2 AccT;     // per-point accumulation of the nearest-neighbour scenes; the projective driver uses AccP
 
 // Warp reduction of 32 values per lane that leaves, in lane L, the warp-wide sum of value L:
 // at each butterfly step a lane keeps one half of its values and ships the other half, so the
@@ -779,21 +758,13 @@ __device__ __forceinline__ void sts32(unsigned addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
-// one scene record: PR_REC 2 = a single 256-bit load (LDG.E.256, sm_100), 1 = two 128-bit loads of the same sector
-#ifndef PR_REC
-#define PR_REC 2
-#endif
+// one scene record with a single 256-bit load (LDG.E.256, sm_100); two 128-bit loads of the same sector: +5 %
 __device__ __forceinline__ void load_rec(const PackedScene& s, int idx, float4& A, float2& B) {
     const float4* r = s.rec + 2 * (size_t)(unsigned)idx;
-#if PR_REC == 2
     float u0 = 0.f, u1 = 0.f;       // padding words of the record
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(A.x), "=f"(A.y), "=f"(A.z), "=f"(A.w), "=f"(B.x), "=f"(B.y), "=f"(u0), "=f"(u1) : "l"(r));
     (void)u0; (void)u1;
-#else
-    A = __ldg(r);
-    B = __ldg(reinterpret_cast<const float2*>(r + 1));
-#endif
 }
 __device__ __forceinline__ void transform(const float* T, float x, float y, float z, float& px, float& py, float& pz) {
     // transform_pcd_cuda (icp.cu:147-149) with the accumulated transform
@@ -813,66 +784,13 @@ __device__ __forceinline__ float fast_rcp(float z) {
 }
 
 // 32*kIlp consecutive points of a tile against the packed projective scene: lane l owns points
-// l, 32+l, 64+l, ..., so each of the four gather instructions covers 32 CONSECUTIVE model points --
-// neighbouring scene pixels, i.e. 4 cache lines per 128-bit gather instead of 16.  The four gathers
-// are issued before any of them is consumed.
+// l, 32+l, 64+l, ..., so each gather instruction covers 32 CONSECUTIVE model points -- neighbouring scene
+// pixels.  The kIlp gathers of a lane are issued before any of them is consumed.
 // Pixel selection: u = int(px/pz*fx + cx + 0.5) (common.h:63-73) evaluated as
 // fma(px*(1/pz), fx, cx+0.5), within 2 ulp of the reference's operation order.  "0 <= int(v) < W" is
 // tested on the truncated integers as unsigned compares; fmaxf(v, -2) first turns NaN into a
 // rejected value (a plain float->int conversion would turn NaN into pixel 0).
-template <bool TAIL>
-__device__ __forceinline__ void group_projective(const PackedScene& s, unsigned addr, unsigned first, unsigned n,
-                                                 const float* T, AccT& acc) {
-    float px[kIlp], py[kIlp], pz[kIlp];
-    int idx[kIlp];
-    bool ok[kIlp];
-#pragma unroll
-    for (int k = 0; k < kIlp; k++) {
-        const float x = lds32(addr + 384 * k), y = lds32(addr + 384 * k + 4), z = lds32(addr + 384 * k + 8);
-        transform(T, x, y, z, px[k], py[k], pz[k]);
-        const float rz = fast_rcp(pz[k]);
-        const int ui = __float2int_rz(fmaxf(fmaf(px[k] * rz, s.fx, s.cx05), -2.0f));
-        const int vi = __float2int_rz(fmaxf(fmaf(py[k] * rz, s.fy, s.cy05), -2.0f));
-        ok[k] = ((unsigned)ui < (unsigned)s.W) & ((unsigned)vi < (unsigned)s.H);
-        if (TAIL) ok[k] = ok[k] & (first + 32 * k < n);
-        idx[k] = vi * s.W + ui;
-    }
-    float4 A[kIlp];
-    float2 B[kIlp];
-#pragma unroll
-    for (int k = 0; k < kIlp; k++) {
-        if (ok[k]) {
-            load_rec(s, idx[k], A[k], B[k]);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < kIlp; k++) {
-        if (ok[k]) {
-            if (A[k].z > 0.f && fabsf(pz[k] - A[k].z) <= s.max_dist) {       // depth_scene.h:42
-                Corr cr;
-                cr.qx = A[k].x; cr.qy = A[k].y; cr.qz = A[k].z; cr.nx = A[k].w; cr.ny = B[k].x; cr.nz = B[k].y;
-                acc_add(acc, px[k], py[k], pz[k], cr);
-            }
-        }
-    }
-}
 
-
-// one warp tile (n <= kWTile points at shared address `tile`), packed projective scene
-__device__ __forceinline__ void compute_tile(const PackedScene& s, unsigned tile, unsigned n, const float* T, AccT& acc) {
-    const unsigned lane = threadIdx.x & 31;
-    unsigned addr = tile + 12 * lane;
-    unsigned first = lane;                         // index of this lane's first point in the group
-    constexpr unsigned kGroup = 32 * kIlp;
-    static_assert(kWTile % kGroup == 0, "a tail group must not read past the tile");
-    const unsigned n_full = n - n % kGroup;
-#pragma unroll 1
-    for (; first < n_full; first += kGroup, addr += 12 * kGroup) group_projective<false>(s, addr, first, n, T, acc);
-    if (n_full < n) group_projective<true>(s, addr, first, n, T, acc);
-}
-
-
-#if PR_PAIR
 // 1/z with the sign folded in: returns -(1/z) refined by one Newton step.  Bit for bit the negation of
 // fast_rcp(z) (rcp.approx is odd, (-z)*r == z*(-r), and round-to-nearest is symmetric).
 __device__ __forceinline__ f2_t fast_nrcp2(f2_t z) {
@@ -1006,7 +924,6 @@ __device__ __noinline__ float slow_item(const PackedScene& s, const float* __res
     }
     return warp_transpose_reduce(v);
 }
-#endif
 
 // one warp tile, any scene with a per-point query() (nearest neighbour)
 template <class SceneT>
@@ -1074,11 +991,7 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
                       HypState* state, float* partials, SceneT scene, pr_icp_criteria crit,
                       pr_registration_result* results) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-#if PR_PAIR
     using AccK = typename std::conditional<std::is_same<SceneT, PackedScene>::value, AccP, AccT>::type;
-#else
-    using AccK = AccT;
-#endif
     constexpr int kWTile = TileOf<SceneT>::kPoints;     // shadows the projective constant on purpose
     constexpr int kWTileFloats = kWTile * 3;
     constexpr int kWTileBytes = kWTileFloats * 4;
@@ -1195,11 +1108,9 @@ icp_persistent_kernel(const float* __restrict__ pts, size_t capacity_points, con
             float v[32];
             acc_unpack(acc, v);
             float mine = warp_transpose_reduce(v);             // lane l = sum of value l
-#if PR_PAIR
             if constexpr (std::is_same<SceneT, PackedScene>::value) {
                 if (__any_sync(0xffffffffu, mine != mine)) mine = slow_item(scene, g, n_pts, T);
             }
-#endif
             __stcg(partials + (size_t)c * kPartialStride + lane, mine);
             take_ticket(st, info.w, h);
         }
