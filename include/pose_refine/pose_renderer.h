@@ -3,6 +3,7 @@
 // FULL-resolution projection matrix, exactly as pose_renderer.cpp:25-36 does.
 #pragma once
 #include "cuda_renderer/renderer.h"
+#include "cuda_icp/icp.h"
 
 class PoseRenderer {
 public:
@@ -27,5 +28,39 @@ public:
         const int w = int(width / down_sample), h = int(height / down_sample);
         auto raw = cuda_renderer::render(tris, init_poses, (size_t)w, (size_t)h, proj_mat);
         return cuda_renderer::raw2mask_uint8_cuda(raw, w, h, init_poses.size());
+    }
+};
+
+// One-call refinement of a batch of pose hypotheses: what the reference's test.cpp does
+// per hypothesis -- render_cuda_keep_in_gpu -> depth2cloud_cuda -> ICP_Point2Plane_cuda (test.cpp:143-172) -- for all
+// hypotheses at once, over pr_refiner_* (mesh uploaded once, all buffers preallocated, one kernel chain per batch).
+class PoseRefiner {
+    pr_refiner* r_ = nullptr;
+public:
+    // tris in model units (mm), K row-major 3x3; max_hyp bounds the batch size
+    PoseRefiner(const std::vector<cuda_renderer::Model::Triangle>& tris, int width, int height, const float* K, size_t max_hyp) {
+        pose_refine::check(pr_refiner_create(&r_, reinterpret_cast<const float*>(tris.data()), tris.size(), (uint32_t)width, (uint32_t)height,
+                                             K, max_hyp, 0), "pr_refiner_create");
+    }
+    ~PoseRefiner() { pr_refiner_destroy(r_); }
+    PoseRefiner(const PoseRefiner&) = delete;
+    PoseRefiner& operator=(const PoseRefiner&) = delete;
+    // Scene_projective::init_Scene_projective_cuda / Scene_nn::init_Scene_nn_cuda of a host depth image (mm)
+    void set_scene_projective(const pose_refine::DepthImage& depth, float max_dist_diff = 0.1f) {
+        pose_refine::check(pr_refiner_set_scene_projective(r_, depth.data, depth.is_int32, max_dist_diff), "pr_refiner_set_scene_projective");
+    }
+    void set_scene_nn(const pose_refine::DepthImage& depth) {
+        pose_refine::check(pr_refiner_set_scene_nn(r_, depth.data, depth.is_int32), "pr_refiner_set_scene_nn");
+    }
+    // poses: model -> camera, row-major 4x4 (mm).  result[i].transformation_ is the ICP update of hypothesis i in
+    // metres (apply it to the cloud of pose i, as ICP_Point2Plane_cuda's result is used upstream).
+    std::vector<cuda_icp::RegistrationResult> refine(const std::vector<cuda_renderer::Model::mat4x4>& poses,
+                                                     const cuda_icp::ICPConvergenceCriteria& c = cuda_icp::ICPConvergenceCriteria()) {
+        std::vector<cuda_icp::RegistrationResult> out(poses.size());
+        if (poses.empty()) return out;
+        const pr_icp_criteria crit = {c.relative_fitness_, c.relative_rmse_, c.max_iteration_};
+        pose_refine::check(pr_refiner_run(r_, reinterpret_cast<const float*>(poses.data()), poses.size(), crit,
+                                          reinterpret_cast<pr_registration_result*>(out.data()), nullptr), "pr_refiner_run");
+        return out;
     }
 };
