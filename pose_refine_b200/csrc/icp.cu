@@ -362,6 +362,9 @@ __device__ __forceinline__ f2_t pk2(float lo, float hi) { f2_t r; asm("mov.b64 %
 __device__ __forceinline__ f2_t bc2(float a) { return pk2(a, a); }
 __device__ __forceinline__ void unpk2(f2_t a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); }
 __device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) { f2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+// acc += a * b with the accumulator as a read-write operand: input and output are the same register pair by
+// construction, so ptxas has no loop-carried copies to insert at the back edge of the group loop
+__device__ __forceinline__ void fma2_acc(f2_t& acc, f2_t a, f2_t b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
 __device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) { f2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f2_t sub2(f2_t a, f2_t b) { f2_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f2_t neg2(f2_t a) {
@@ -396,10 +399,10 @@ __device__ __forceinline__ void accumulate_pair(AccP& a, f2_t px, f2_t py, f2_t 
 #pragma unroll
     for (int i = 0; i < 6; i++)
 #pragma unroll
-        for (int j = i; j < 6; j++) { a.s[k] = fma2(J[i], J[j], a.s[k]); k++; }
+        for (int j = i; j < 6; j++) { fma2_acc(a.s[k], J[i], J[j]); k++; }
 #pragma unroll
-    for (int i = 0; i < 6; i++) a.s[21 + i] = fma2(J[i], r, a.s[21 + i]);
-    a.s[27] = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, a.s[27])));
+    for (int i = 0; i < 6; i++) fma2_acc(a.s[21 + i], J[i], r);
+    fma2_acc(a.s[27], dx, dx); fma2_acc(a.s[27], dy, dy); fma2_acc(a.s[27], dz, dz);
 }
 
 __device__ __forceinline__ void acc_zero(Acc2& a) { zero_acc2(a); }
