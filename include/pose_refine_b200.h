@@ -137,6 +137,7 @@ int pr_render_indexed_batch(const float* verts_dev, size_t n_verts, const int32_
 /* out_pts_dev[3*offsets[i] .. 3*(offsets[i]+counts[i])): the same points depth2cloud_cuda produces, ordered     */
 /* tile by tile (64x64-pixel screen tiles in row-major order, row-major inside a tile) instead of row-major      */
 /* over the image.  counts / offsets / overflow / capacity_points / align_points as in pr_depth2cloud_count.     */
+/* out_pts_dev == NULL: depth only (K, counts, offsets may then be NULL) -- pr_render_indexed_batch with clusters.  */
 /* Optional acceleration structure for it (no upstream counterpart): pr_mesh_cluster (host) reorders the faces of an   */
 /* indexed mesh along a Morton curve of their centroids, cuts them into clusters of 64 consecutive triangles and       */
 /* lists every cluster's unique vertices.  With the lists on the device (pr_mesh_clusters) the rasteriser bins          */

@@ -183,6 +183,28 @@ def mesh_cluster(verts, faces):
     return faces, off, cv[: off[-1]].copy()
 
 
+def render_clustered_keep_in_gpu(verts, faces, poses, width, height, proj_mat, clusters, out=None, ws=None):
+    """Depth only through the cluster-binned rasteriser (pr_render_cloud_batch without clouds): same output as
+    render_indexed_keep_in_gpu.  verts / faces / poses may be device tensors; out / ws can be reused between calls."""
+    _require_device()
+    verts = _dev(verts, torch.float32).reshape(-1, 3)
+    faces = _dev(faces, torch.int32).reshape(-1, 3)
+    proj = _f32c(proj_mat).reshape(16)
+    poses_t = _dev(poses, torch.float32).reshape(-1, 16)
+    n_poses = poses_t.shape[0]
+    off_d, cv_d = _dev(clusters[0], torch.int32), _dev(clusters[1], torch.int32)
+    cl = _lib.MeshClusters(off_d.shape[0] - 1, off_d.data_ptr(), cv_d.data_ptr())
+    if out is None:
+        out = torch.empty((n_poses, height, width), dtype=torch.int32, device="cuda")
+    ws_bytes = lib().pr_render_cloud_workspace_bytes(n_poses, verts.shape[0], faces.shape[0], width, height)
+    if ws is None or ws.numel() < ws_bytes:
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    check(lib().pr_render_cloud_batch(verts.data_ptr(), verts.shape[0], faces.data_ptr(), faces.shape[0], poses_t.data_ptr(), 1,
+                                      n_poses, width, height, proj.ctypes.data, None, out.data_ptr(), None, 0, 4, None, None, None,
+                                      C.cast(C.pointer(cl), C.c_void_p), ws.data_ptr(), ws.numel(), _stream()), "pr_render_cloud_batch")
+    return out
+
+
 def render_cloud_batch(verts, faces, poses, width, height, proj_mat, K, capacity_points=None, align_points=4, clusters=None):
     """Fused render_cuda_keep_in_gpu + depth2cloud_cuda per pose (pr_render_cloud_batch).
     clusters: (vert_off, cluster_verts) from mesh_cluster -- faces must then be mesh_cluster's reordered faces.

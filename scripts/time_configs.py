@@ -64,7 +64,17 @@ def render_soup():      # pr_render_batch with preallocated output and workspace
 
 
 ms_soup = timed(render_soup)
+# clustered: indexed mesh, Morton-ordered 64-triangle clusters (device-resident mesh, reused output / workspace)
+verts, faces = api.mesh_index(tris)
+cf, off, cv = api.mesh_cluster(verts, faces)
+v_d, f_d = torch.as_tensor(verts).cuda(), torch.as_tensor(cf).cuda()
+cl_d = (torch.as_tensor(off).cuda(), torch.as_tensor(cv).cuda())
+ws_c = torch.empty(L.pr_render_cloud_workspace_bytes(P5, verts.shape[0], n_tris, 640, 480), dtype=torch.uint8, device="cuda")
+depth_c = torch.empty_like(depth)
+ms_cl = timed(lambda: api.render_clustered_keep_in_gpu(v_d, f_d, p5, 640, 480, proj5, cl_d, out=depth_c, ws=ws_c))
+assert torch.equal(depth, depth_c)
 out["c5_render"] = {"poses": P5, "tris": n_tris, "render_ms": round(ms_soup, 3), "poses_per_s": round(P5 / ms_soup * 1e3, 1),
+                    "clustered_render_ms": round(ms_cl, 3), "clustered_poses_per_s": round(P5 / ms_cl * 1e3, 1),
                     "depth_write_GBs": round(P5 * 640 * 480 * 4 / (ms_soup * 1e-3) / 1e9, 1),
                     "valid_px_per_pose": round(float((depth > 0).sum()) / P5, 1)}
 print(json.dumps(out))

@@ -180,6 +180,8 @@ def test_render_clustered_edge_cases(api, port, golden):
             assert set(cf[64 * c: 64 * c + 64].reshape(-1).tolist()) == set(cv[off[c]: off[c + 1]].tolist())
         depth, _, _, _ = api.render_cloud_batch(v, cf, ps, 640, 480, arrays["proj"], K, clusters=(off, cv))
         assert np.array_equal(depth.cpu().numpy(), port.render(tris, ps, 640, 480, arrays["proj"]))
+        assert np.array_equal(api.render_clustered_keep_in_gpu(v, cf, ps, 640, 480, arrays["proj"], (off, cv)).cpu().numpy(),
+                              port.render(tris, ps, 640, 480, arrays["proj"]))
 
 
 def test_render_big_triangles_overflowing_bins(api, port, golden):
