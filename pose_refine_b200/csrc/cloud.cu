@@ -12,6 +12,8 @@
 //   scan  : per image, exclusive scan over its segments (in place) + image total -> counts
 //   offs  : exclusive scan over images of the padded totals -> offsets[n_images+1]
 //   fill  : per segment, intra-CTA scan + scatter of back-projected points
+// Fused with the rasteriser (pr_render_cloud_batch -> cloud_from_tiles): the tile write-out has already counted the
+// valid pixels, so tile_scan_kernel + cloud_fill_tiles_kernel only visit the non-empty screen tiles (tile-major order).
 #include "common.cuh"
 #include <limits.h>
 

@@ -9,9 +9,9 @@
 // non-contractable IEEE ops.  Results equal the reference's CPU arrays bit for bit.
 //
 // Nearest-neighbour scene (Scene_nn::init_Scene_nn_cuda, pcd_scene.cu:3-20 -> pcd_scene.cpp:4-184):
-// normals and back-projection on the device, compaction + kd-tree build on the host with the
-// reference's level-by-level midpoint-split algorithm, so the 52-byte node array is
-// interchangeable with KDTree_cpu's.
+// normals and back-projection on the device; compaction + kd-tree build either on the device
+// (pr_scene_nn_build: kd_* kernels below, the same tree node for node) or on the host with the
+// reference's level-by-level algorithm (pr_scene_nn_build_host, upstream's way).
 #include "common.cuh"
 #include <float.h>
 #include <limits.h>
