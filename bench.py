@@ -15,9 +15,11 @@ One JSON line on stdout (rank 0):
           results D2H inside the timed region
   roofline    the ICP pass kernel: algorithmic bytes per launch / mean launch time vs measured HBM peak
   cpu_baseline  the CPU oracle (reference build when present) on a bounded sample, same run
+  ref_cuda_build  the reference's own CUDA path (its .cu files compiled unmodified for sm_100, oracle/_ref) on a bounded
+          sample of the same workload on this GPU, in a child process -- the "reference CUDA build" of north_star's 10x target
 
 `--impl reference` times the reference's own CPU path on the host cores instead (oracle/_ref when
-it was built, else the oracle port) -- the only place bench.py executes oracle/.
+it was built, else the oracle port) -- with cpu_baseline and ref_cuda_build the only places bench.py executes oracle/.
 """
 import argparse
 import json
