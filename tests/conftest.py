@@ -42,7 +42,11 @@ def _checker(kind):
             import subprocess
             subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, capture_output=True)
         else:
-            pytest.skip("oracle/_ref/libpose_refine_ref.so not built (needs /root/reference)")
+            import subprocess
+            if os.path.isdir("/root/reference/cuda_icp"):      # build the checker where the reference is mounted
+                subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True, capture_output=True)
+            if not binding.available(kind):
+                pytest.skip("oracle/_ref/libpose_refine_ref.so not built (needs /root/reference)")
     chk = binding.load(kind)
     chk.set_threads(1)
     return chk
