@@ -142,3 +142,17 @@ def test_mesh_cluster_host(golden):
         ext.append((p.max(0) - p.min(0)).max())
     full = (verts.max(0) - verts.min(0)).max()
     assert np.median(ext) < 0.2 * full                      # clusters are spatially compact
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/pose_refine_b200.h must compile as C99 (no C++-only constructs, no CUDA or
+    torch types in the signatures) as well as C++14."""
+    import os, subprocess
+    from conftest import ROOT
+    src = tmp_path / "h.c"
+    src.write_text('#include "pose_refine_b200.h"\nint main(void) { pr_registration_result r; (void)r; return pr_version() < 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, "-fsyntax-only", str(src)],
+                ["/usr/bin/g++", "-std=c++14", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)]):
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
