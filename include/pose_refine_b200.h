@@ -34,6 +34,7 @@ extern "C" {
 #define PR_ERR_CAPACITY (-4)
 #define PR_ERR_IO (-5)
 #define PR_ERR_NO_DEVICE (-6)
+#define PR_ERR_COMM (-7)          /* NCCL missing (libnccl.so.2 could not be loaded) or an NCCL call failed */
 
 typedef struct CUstream_st* pr_stream_t;
 
@@ -220,6 +221,9 @@ int pr_scene_nn_build(const void* depth_dev, int depth_is_int32, uint32_t width,
 /*   results_dev n_hyp records; flags: PR_ICP_UPDATE_POINTS writes the refined points back        */
 /*               (the reference mutates the model cloud in place, icp.cu:209).                    */
 #define PR_ICP_UPDATE_POINTS 1
+/* cross-check driver: one launch per pass, every operation in the reference's own order (IEEE divisions, the        */
+/* reference's stackless kd-tree walk, Eigen's pivoted LDL^T).  Several times slower; same results within tolerance.  */
+#define PR_ICP_REFERENCE_ARITHMETIC 2
 /* scene_pixels: width*height of the projective scene the workspace will be used with; for Scene_nn pass   */
 /* n_points + 2*n_nodes + 16 (room for the re-laid-out kd-tree; with less, the reference-layout walk is used). */
 size_t pr_icp_workspace_bytes(size_t n_hyp, size_t capacity_points, size_t scene_pixels);
@@ -232,6 +236,17 @@ int pr_icp_nn_batch(float* pts_dev, const uint32_t* offsets_dev, const uint32_t*
                     pr_registration_result* results_dev, int flags,
                     void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
 
+/* The projective scene as the ICP kernel gathers it: one 32-byte record {q.xyz, n.xyz, 0, 0} per pixel (one L2 sector  */
+/* per correspondence).  pr_icp_projective_batch re-packs the scene into its workspace on every call;                  */
+/* a caller that refines many batches against one scene packs once (packed_dev: 32-byte aligned,                       */
+/* pr_scene_projective_packed_bytes bytes) and calls the _packed variant (packed_dev == NULL: same as the plain call).  */
+size_t pr_scene_projective_packed_bytes(uint32_t width, uint32_t height);
+int pr_scene_projective_pack(const pr_scene_projective* scene, void* packed_dev, pr_stream_t stream);
+int pr_icp_projective_batch_packed(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_dev, size_t n_hyp,
+                                   size_t capacity_points, const pr_scene_projective* scene, const void* packed_dev,
+                                   pr_icp_criteria criteria, pr_registration_result* results_dev, int flags,
+                                   void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
+
 /* eigen_slover_666 (icp.cpp:29-45) on the host: A 6x6 symmetric (36 floats), b 6 -> row-major 4x4. */
 int pr_solve_666(const float A[36], const float b[6], float T[16]);
 
@@ -240,6 +255,27 @@ int pr_solve_666(const float A[36], const float b[6], float T[16]);
 int pr_pcd2ab_projective(const float* pts_dev, size_t n, const pr_scene_projective* scene, float* out29_dev,
                          pr_stream_t stream);
 int pr_pcd2ab_nn(const float* pts_dev, size_t n, const pr_scene_nn* scene, float* out29_dev, pr_stream_t stream);
+
+/* Parity entry points onto the SHIPPED ICP kernel (the two above run the reference-arithmetic kernel).               */
+/*   pr_pass_sums_*:  one evaluation pass (identity transform) of pr_icp_*_batch's own kernel over a ragged batch;     */
+/*                    out32_dev[32*h .. 32*h+28] = the 29 sums of hypothesis h (icp.cu:170-172).  Arguments as         */
+/*                    pr_icp_*_batch.                                                                                 */
+/*   pr_correspondences_*: for every point, the scene index that kernel's search picks (projective: pixel u + v*W     */
+/*                    after the depth gate, depth_scene.h:30-48; nn: index into the leaf-ordered scene points,        */
+/*                    pcd_scene.h:61-136), -1 = no valid correspondence.  idx_dev: n int32.  workspace as pr_icp_*.    */
+/*   pr_solve_666_device: n systems, one device thread each, S29_dev[29*i..] in thrust__pcd2Ab's order ->             */
+/*                    E16_dev[16*i..]; fast = 1: the solver the kernel runs between passes, 0: Eigen's pivoted LDL^T.   */
+int pr_pass_sums_projective(const float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_dev, size_t n_hyp,
+                            size_t capacity_points, const pr_scene_projective* scene, float* out32_dev,
+                            void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
+int pr_pass_sums_nn(const float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_dev, size_t n_hyp,
+                    size_t capacity_points, const pr_scene_nn* scene, float* out32_dev,
+                    void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
+int pr_correspondences_projective(const float* pts_dev, size_t n, const pr_scene_projective* scene, int32_t* idx_dev,
+                                  void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
+int pr_correspondences_nn(const float* pts_dev, size_t n, const pr_scene_nn* scene, int32_t* idx_dev,
+                          void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
+int pr_solve_666_device(const float* S29_dev, size_t n, int fast, float* E16_dev, pr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------- */
 /* pr_refiner: the whole path for one mesh + one scene behind a single call with HOST buffers -- */
@@ -254,9 +290,15 @@ typedef struct pr_refiner pr_refiner;
 int pr_refiner_create(pr_refiner** out, const float* tris_host, size_t n_tris, uint32_t width, uint32_t height,
                       const float K[9], size_t max_hyp, size_t capacity_points);
 void pr_refiner_destroy(pr_refiner* r);
-/* Scene from a HOST depth image (uint16 or int32, mm), prepared on the device.                  */
+/* Scene from a HOST depth image (uint16 or int32, mm), prepared on the device.  Synchronous (copy + preparation +   */
+/* cudaStreamSynchronize on the default stream).  Scene buffers are allocated on first use and then kept.            */
 int pr_refiner_set_scene_projective(pr_refiner* r, const void* depth_host, int depth_is_int32, float max_dist_diff);
 int pr_refiner_set_scene_nn(pr_refiner* r, const void* depth_host, int depth_is_int32);
+/* Scene from a DEVICE depth image (e.g. one that arrived by pr_broadcast_scene): no host copy.  The projective        */
+/* variant is asynchronous on `stream`; the kd-tree variant synchronises (pr_scene_nn_build reads the level sizes).  */
+int pr_refiner_set_scene_projective_device(pr_refiner* r, const void* depth_dev, int depth_is_int32, float max_dist_diff,
+                                           pr_stream_t stream);
+int pr_refiner_set_scene_nn_device(pr_refiner* r, const void* depth_dev, int depth_is_int32, pr_stream_t stream);
 /* poses_host: n_hyp row-major 4x4 (model -> camera, mm).  results_host: n_hyp records.           */
 /* Copies poses H2D, runs render -> cloud -> ICP on `stream`, copies results D2H, synchronises.    */
 int pr_refiner_run(pr_refiner* r, const float* poses_host, size_t n_hyp, pr_icp_criteria criteria,
@@ -270,6 +312,34 @@ int pr_refiner_buffers(pr_refiner* r, const int32_t** depth_dev, const float** p
                        const uint32_t** offsets_dev, const uint32_t** counts_dev);
 /* kernel launches issued by this library since load (all entry points), for bench accounting.    */
 uint64_t pr_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Multi-GPU (no upstream counterpart: the reference is single-GPU, README.md:15 only suggests host threads).      */
+/* The batch shards by hypothesis -- one process or host thread per GPU, no collective in the data path:            */
+/*   pr_shard_plan       contiguous shards whose sizes differ by at most one: rank r owns [begin, begin + count)     */
+/*   pr_broadcast_scene  the scene depth image (any device buffer) from `root` to every rank, in place               */
+/*                       (ncclBroadcast on `stream`); each rank then prepares the scene on its own GPU               */
+/*                       (pr_scene_projective_init / pr_refiner_set_scene_*_device), bit-identically                 */
+/*   pr_gather_results   n_per_rank records of every rank -> all_dev[nranks * n_per_rank] on every rank              */
+/*                       (ncclAllGather; pad the shards to the largest one).  Starts when the work queued on         */
+/*                       `stream` so far is complete and runs on the communicator's own stream, so the caller's      */
+/*                       next batch overlaps it; pr_gather_wait makes `stream` (host_sync = 0) or the host           */
+/*                       (host_sync = 1) wait for it.                                                                */
+/* NCCL is loaded at run time (dlopen libnccl.so.2); without it these return PR_ERR_COMM.  A communicator is made     */
+/* from an ncclUniqueId (128 bytes, created on one rank by pr_nccl_unique_id and handed to the others by the host's   */
+/* own means) or adopted from an existing ncclComm_t.                                                                 */
+typedef struct pr_comm pr_comm;
+int pr_device_count(int* count);
+int pr_set_device(int device);
+int pr_shard_plan(size_t n_hyp, int nranks, int rank, size_t* begin, size_t* count);
+int pr_nccl_unique_id(void* id128);
+int pr_comm_create(pr_comm** out, const void* id128, int nranks, int rank);     /* ncclCommInitRank on the current device */
+int pr_comm_adopt(pr_comm** out, void* nccl_comm, int nranks, int rank);        /* an existing ncclComm_t; not destroyed  */
+void pr_comm_destroy(pr_comm* comm);
+int pr_broadcast_scene(pr_comm* comm, void* buf_dev, size_t bytes, int root, pr_stream_t stream);
+int pr_gather_results(pr_comm* comm, const pr_registration_result* local_dev, size_t n_per_rank,
+                      pr_registration_result* all_dev, pr_stream_t stream);
+int pr_gather_wait(pr_comm* comm, pr_stream_t stream, int host_sync);
 
 #ifdef __cplusplus
 }

@@ -73,16 +73,45 @@ PROTOTYPES = {
     "pr_refiner_run_device": (_i, [_vp, _vp, _sz, Criteria, _vp, _vp]),
     "pr_refiner_buffers": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "pr_launch_count": (C.c_uint64, []),
+    "pr_scene_projective_packed_bytes": (_sz, [_u32, _u32]),
+    "pr_scene_projective_pack": (_i, [C.POINTER(SceneProjective), _vp, _vp]),
+    "pr_icp_projective_batch_packed": (_i, [_vp, _vp, _vp, _sz, _sz, C.POINTER(SceneProjective), _vp, Criteria, _vp, _i, _vp, _sz, _vp]),
+    "pr_pass_sums_projective": (_i, [_vp, _vp, _vp, _sz, _sz, C.POINTER(SceneProjective), _vp, _vp, _sz, _vp]),
+    "pr_pass_sums_nn": (_i, [_vp, _vp, _vp, _sz, _sz, C.POINTER(SceneNN), _vp, _vp, _sz, _vp]),
+    "pr_correspondences_projective": (_i, [_vp, _sz, C.POINTER(SceneProjective), _vp, _vp, _sz, _vp]),
+    "pr_correspondences_nn": (_i, [_vp, _sz, C.POINTER(SceneNN), _vp, _vp, _sz, _vp]),
+    "pr_solve_666_device": (_i, [_vp, _sz, _i, _vp, _vp]),
+    "pr_refiner_set_scene_projective_device": (_i, [_vp, _vp, _i, _f, _vp]),
+    "pr_refiner_set_scene_nn_device": (_i, [_vp, _vp, _i, _vp]),
+    "pr_device_count": (_i, [C.POINTER(_i)]),
+    "pr_set_device": (_i, [_i]),
+    "pr_shard_plan": (_i, [_sz, _i, _i, C.POINTER(_sz), C.POINTER(_sz)]),
+    "pr_nccl_unique_id": (_i, [_vp]),
+    "pr_comm_create": (_i, [C.POINTER(_vp), _vp, _i, _i]),
+    "pr_comm_adopt": (_i, [C.POINTER(_vp), _vp, _i, _i]),
+    "pr_comm_destroy": (None, [_vp]),
+    "pr_broadcast_scene": (_i, [_vp, _vp, _sz, _i, _vp]),
+    "pr_gather_results": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "pr_gather_wait": (_i, [_vp, _vp, _i]),
 }
 
 _dll = None
+_path = LIB
+
+
+def use_library(path):
+    """Experiment scripts: bind an alternative build of the same library (scripts/build_variants.py) before first use."""
+    global _path
+    if _dll is not None:
+        raise RuntimeError("the library is already loaded")
+    _path = path
 
 
 def lib():
     """The loaded library; raises (never falls back) when it has not been built."""
     global _dll
     if _dll is None:
-        path = os.environ.get("PR_LIB", LIB)   # experiments: alternative builds of the same library
+        path = _path
         if not os.path.exists(path):
             raise ImportError(
                 f"{LIB} is missing: build it with `python -m pose_refine_b200.build` "

@@ -401,9 +401,16 @@ class SceneNN:
 
 # ---------------------------------------------------------------------------------------------
 # ICP
-def icp_batch(pts, offsets, counts, scene, criteria=None, update_points=False):
+def _icp_workspace(P, cap, scene):
+    n_px = scene.width * scene.height if isinstance(scene, SceneProjective) else scene.pcd.shape[0] + 2 * len(scene.nodes_host) + 16
+    ws_bytes = lib().pr_icp_workspace_bytes(P, cap, n_px)
+    return torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device="cuda"), ws_bytes
+
+
+def icp_batch(pts, offsets, counts, scene, criteria=None, update_points=False, reference_arithmetic=False):
     """Batched ICP_Point2Plane_cuda: pts cuda [cap,3]; offsets/counts cuda int32 -> cuda float32 [P,18]
-    (row-major 4x4, inlier_rmse_, fitness_ per hypothesis)."""
+    (row-major 4x4, inlier_rmse_, fitness_ per hypothesis).  reference_arithmetic: the cross-check driver
+    (PR_ICP_REFERENCE_ARITHMETIC: one launch per pass, every operation in the reference's order)."""
     _require_device()
     criteria = criteria or ICPConvergenceCriteria()
     assert pts.is_cuda and pts.dtype == torch.float32 and pts.is_contiguous()
@@ -411,10 +418,8 @@ def icp_batch(pts, offsets, counts, scene, criteria=None, update_points=False):
     P = counts.shape[0]
     cap = pts.shape[0]
     res = torch.empty((max(P, 1), 18), dtype=torch.float32, device="cuda")
-    n_px = scene.width * scene.height if isinstance(scene, SceneProjective) else scene.pcd.shape[0] + 2 * len(scene.nodes_host) + 16
-    ws_bytes = lib().pr_icp_workspace_bytes(P, cap, n_px)
-    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device="cuda")
-    flags = 1 if update_points else 0
+    ws, ws_bytes = _icp_workspace(P, cap, scene)
+    flags = (1 if update_points else 0) | (2 if reference_arithmetic else 0)
     sc = scene.c()
     if isinstance(scene, SceneProjective):
         rc = lib().pr_icp_projective_batch(pts.data_ptr(), offsets.data_ptr(), counts.data_ptr(), P, cap, C.byref(sc),
@@ -436,8 +441,49 @@ def ICP_Point2Plane_cuda(model_pcd, scene, criteria=None):
     return RegistrationResult(res[:16].reshape(4, 4).copy(), float(res[16]), float(res[17]))
 
 
+def pass_sums(pts, offsets, counts, scene):
+    """One evaluation pass of the SHIPPED ICP kernel (identity transform) over a ragged batch -> [P,29] float32 (host):
+    the 29 sums of thrust__pcd2Ab per hypothesis (pr_pass_sums_*)."""
+    _require_device()
+    assert pts.is_cuda and pts.dtype == torch.float32 and pts.is_contiguous()
+    offsets, counts = _dev(offsets, torch.int32), _dev(counts, torch.int32)
+    P, cap = counts.shape[0], pts.shape[0]
+    out = torch.zeros((max(P, 1), 32), dtype=torch.float32, device="cuda")
+    ws, ws_bytes = _icp_workspace(P, cap, scene)
+    sc = scene.c()
+    fn = lib().pr_pass_sums_projective if isinstance(scene, SceneProjective) else lib().pr_pass_sums_nn
+    check(fn(pts.data_ptr(), offsets.data_ptr(), counts.data_ptr(), P, cap, C.byref(sc), out.data_ptr(), ws.data_ptr(), ws_bytes,
+             _stream()), "pr_pass_sums")
+    return out[:P, :29].cpu().numpy()
+
+
+def correspondences(pts, scene):
+    """For every point of a cloud, the scene index the shipped kernel's search picks (-1: none) -> int32 [n] (host).
+    Projective: pixel u + v*W after the depth gate; nn: index into the leaf-ordered scene points."""
+    _require_device()
+    pts = _dev(pts, torch.float32).reshape(-1, 3)
+    n = pts.shape[0]
+    idx = torch.empty(max(n, 1), dtype=torch.int32, device="cuda")
+    ws, ws_bytes = _icp_workspace(1, n, scene)
+    sc = scene.c()
+    fn = lib().pr_correspondences_projective if isinstance(scene, SceneProjective) else lib().pr_correspondences_nn
+    check(fn(pts.data_ptr(), n, C.byref(sc), idx.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "pr_correspondences")
+    return idx[:n].cpu().numpy()
+
+
+def solve_666_device(S29, fast=True):
+    """n normal-equation systems (the 29 sums each, thrust__pcd2Ab's order) solved on the device, one thread each
+    -> [n,4,4] float32.  fast: the solver the ICP kernel runs between passes; else Eigen's pivoted LDL^T restated."""
+    _require_device()
+    S = _dev(_f32c(S29).reshape(-1, 29), torch.float32)
+    n = S.shape[0]
+    E = torch.empty((max(n, 1), 16), dtype=torch.float32, device="cuda")
+    check(lib().pr_solve_666_device(S.data_ptr(), n, int(bool(fast)), E.data_ptr(), _stream()), "pr_solve_666_device")
+    return E[:n].cpu().numpy().reshape(-1, 4, 4)
+
+
 def pcd2ab(pts, scene):
-    """One transform_reduce of thrust__pcd2Ab (icp.cu:170-172) over a cloud -> 29 floats (host)."""
+    """One transform_reduce of thrust__pcd2Ab (icp.cu:170-172) over a cloud -> 29 floats (host); reference-arithmetic kernel."""
     _require_device()
     pts = _dev(pts, torch.float32).reshape(-1, 3)
     out = torch.zeros(32, dtype=torch.float32, device="cuda")
@@ -481,6 +527,19 @@ class PoseRefiner:
         d = np.ascontiguousarray(depth)
         assert d.dtype in (np.int32, np.uint16) and d.shape == (self.height, self.width)
         check(lib().pr_refiner_set_scene_nn(self._h, d.ctypes.data, int(d.dtype == np.int32)), "pr_refiner_set_scene_nn")
+
+    def set_scene_projective_device(self, depth_dev, max_dist_diff=0.1):
+        """Scene from a cuda tensor [H,W] int32 / uint16 (no host copy; asynchronous on the current stream)."""
+        assert depth_dev.is_cuda and depth_dev.dtype in (torch.int32, torch.uint16) and tuple(depth_dev.shape) == (self.height, self.width)
+        depth_dev = depth_dev.contiguous()
+        check(lib().pr_refiner_set_scene_projective_device(self._h, depth_dev.data_ptr(), int(depth_dev.dtype == torch.int32),
+                                                           max_dist_diff, _stream()), "pr_refiner_set_scene_projective_device")
+
+    def set_scene_nn_device(self, depth_dev):
+        assert depth_dev.is_cuda and depth_dev.dtype in (torch.int32, torch.uint16) and tuple(depth_dev.shape) == (self.height, self.width)
+        depth_dev = depth_dev.contiguous()
+        check(lib().pr_refiner_set_scene_nn_device(self._h, depth_dev.data_ptr(), int(depth_dev.dtype == torch.int32), _stream()),
+              "pr_refiner_set_scene_nn_device")
 
     def run(self, poses_host, criteria=None, results_host=None):
         """poses_host: [P,4,4] float32 (numpy or pinned torch) -> results [P,18] host. H2D + D2H inside."""

@@ -1,0 +1,414 @@
+// icp_device.cuh -- device-side building blocks of the ICP kernels (icp.cu): scene views, the two
+// Scene_*::query restatements, the per-point 29-sum term in its three forms, the transposing warp reduction.
+// Split out of icp.cu so that the drivers and the parity/debug kernels share ONE copy of every function.
+#pragma once
+#include "common.cuh"
+#include "solver.cuh"
+#include <float.h>
+#include <limits.h>
+
+namespace prb {
+
+constexpr int kIcpThreads = 256;
+constexpr int kIcpWarps = kIcpThreads / 32;
+constexpr int kPartialStride = 32;   // floats per chunk partial (29 used)
+
+struct alignas(128) HypState {
+    float T[12];            // accumulated transform, rows 0..2 (row 3 = 0 0 0 1)
+    float fitness, rmse;    // values of the previous pass ("backup", icp.cu:179)
+    int done;               // hypothesis has returned
+    int pass;               // passes evaluated so far (= upstream's `iter`)
+    unsigned arrived;       // chunk CTAs that deposited in the current pass
+    unsigned n_chunks;
+    unsigned chunk_begin;   // first chunk id of this hypothesis
+    unsigned pad[9];
+};
+static_assert(sizeof(HypState) == 128, "HypState");
+
+struct ProjScene {
+    int W, H;
+    float fW, fH;
+    float max_dist;
+    float fx, fy, cx, cy;
+    const float* pcd;
+    const float* nrm;
+};
+struct NnScene {
+    float max_dist_sq;
+    const float* pcd;
+    const float* nrm;
+    const pr_node_kdtree* nodes;
+    int n_nodes;
+};
+
+struct Corr { float qx, qy, qz, nx, ny, nz; };
+
+// Scene_projective::query (depth_scene.h:30-48).  The pixel selection uses non-contractable ops so
+// that, for equal p, it picks the same pixel as the CPU build.  int(v) of pcd2dep (common.h:63-73)
+// is truncation; "0 <= int(v) < W" is tested in the float domain as -1 < v < W, which is the same
+// set for finite v and also rejects NaN / out-of-int-range values (x86 gives INT_MIN there).
+__device__ __forceinline__ bool query(const ProjScene& s, float px, float py, float pz, Corr& c) {
+    const float uf = addf(addf(mulf(divf(px, pz), s.fx), s.cx), 0.5f);
+    const float vf = addf(addf(mulf(divf(py, pz), s.fy), s.cy), 0.5f);
+    if (!(uf > -1.0f && uf < s.fW && vf > -1.0f && vf < s.fH)) return false;
+    const size_t idx = (size_t)(int)uf + (size_t)(int)vf * (size_t)s.W;
+    const float* q = s.pcd + 3 * idx;
+    c.qx = __ldg(q); c.qy = __ldg(q + 1); c.qz = __ldg(q + 2);
+    const float dz = pz - c.qz;
+    const float adz = (dz > 0.f) ? dz : -dz;
+    if (c.qz <= 0.f || adz > s.max_dist) return false;
+    const float* n = s.nrm + 3 * idx;
+    c.nx = __ldg(n); c.ny = __ldg(n + 1); c.nz = __ldg(n + 2);
+    return true;
+}
+
+// Scene_nn::query (pcd_scene.h:61-136): the reference's stackless descend / backtrack walk over the
+// 52-byte nodes, including its pruning rule (distance to the RE-VISITED node's box) and its
+// strict-< tie rule (first visited wins).
+__device__ __forceinline__ int nn_search_reference(const NnScene& s, float px, float py, float pz) {
+    if (s.n_nodes <= 0) return -1;
+    bool backtrack = false;
+    int last = -1, cur = 0, best = 0;
+    float best_d2 = FLT_MAX;
+    while (cur >= 0) {
+        const pr_node_kdtree* nd = s.nodes + cur;
+        const int child1 = __ldg(&nd->child1), child2 = __ldg(&nd->child2);
+        if (!backtrack) {
+            if (child1 < 0 || child2 < 0) {
+                const int lo = __ldg(&nd->left), hi = __ldg(&nd->right);
+                for (int i = lo; i < hi; i++) {
+                    const float dx = px - __ldg(s.pcd + 3 * i), dy = py - __ldg(s.pcd + 3 * i + 1), dz = pz - __ldg(s.pcd + 3 * i + 2);
+                    const float d2 = addf(addf(mulf(dx, dx), mulf(dy, dy)), mulf(dz, dz));
+                    if (d2 < best_d2) { best_d2 = d2; best = i; }
+                }
+                backtrack = true; last = cur; cur = __ldg(&nd->parent);
+            } else {
+                const int dim = __ldg(&nd->split_dim);
+                const float sv = __ldg(&nd->split_v);
+                const float diff = (dim == 0 ? px : (dim == 1 ? py : pz)) - sv;
+                last = cur; cur = (diff < 0.f) ? child1 : child2;
+            }
+        } else {
+            const int dim = __ldg(&nd->split_dim);
+            const float sv = __ldg(&nd->split_v);
+            const float diff = (dim == 0 ? px : (dim == 1 ? py : pz)) - sv;
+            const int near_child = (diff < 0.f) ? child1 : child2;
+            const int far_child = (diff < 0.f) ? child2 : child1;
+            float lb = 0.f;
+            const float b0 = __ldg(&nd->bbox[0]), b1 = __ldg(&nd->bbox[1]), b2 = __ldg(&nd->bbox[2]);
+            const float b3 = __ldg(&nd->bbox[3]), b4 = __ldg(&nd->bbox[4]), b5 = __ldg(&nd->bbox[5]);
+            if (px < b0) lb = addf(lb, mulf(b0 - px, b0 - px)); else if (px > b1) lb = addf(lb, mulf(b1 - px, b1 - px));
+            if (py < b2) lb = addf(lb, mulf(b2 - py, b2 - py)); else if (py > b3) lb = addf(lb, mulf(b3 - py, b3 - py));
+            if (pz < b4) lb = addf(lb, mulf(b4 - pz, b4 - pz)); else if (pz > b5) lb = addf(lb, mulf(b5 - pz, b5 - pz));
+            if (last == near_child && lb <= best_d2) { last = cur; cur = far_child; backtrack = false; }
+            else { last = cur; cur = __ldg(&nd->parent); }
+        }
+    }
+    if (!(best_d2 < s.max_dist_sq)) return -1;
+    return best;
+}
+__device__ __forceinline__ bool query(const NnScene& s, float px, float py, float pz, Corr& c) {
+    const int best = nn_search_reference(s, px, py, pz);
+    if (best < 0) return false;
+    c.qx = __ldg(s.pcd + 3 * best); c.qy = __ldg(s.pcd + 3 * best + 1); c.qz = __ldg(s.pcd + 3 * best + 2);
+    c.nx = __ldg(s.nrm + 3 * best); c.ny = __ldg(s.nrm + 3 * best + 1); c.nz = __ldg(s.nrm + 3 * best + 2);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Packed kd-tree for the hypothesis-resident driver.  Same tree (same nodes, same leaf ranges, same points) as
+// the reference's Node_kdtree array, re-laid out per ICP call so that a node is two aligned float4:
+//     {lo.x, lo.y, lo.z, a}   {hi.x, hi.y, hi.z, unused}
+// a >= 0: internal node, children a and a+1 (build_tree appends them together, pcd_scene.cpp:160-170);
+// a <  0: leaf, a = 0x80000000 | count << 24 | left.  [lo,hi] is the box of the node's OWN points --
+// computed here for leaves too (the reference stores none for leaves, pcd_scene.h:14-19).
+// The query is an exact nearest-neighbour search like Scene_nn::query, but it prunes with the box of
+// the CHILD it is about to enter (the reference prunes with the box of the node it re-visits, which is
+// much weaker: 385 node visits per query on the fixture vs ~20-40 here), starts
+// from best = max_dist^2 (anything farther is invalid anyway, pcd_scene.h:127) and keeps the far
+// children on a small explicit stack.  Distances use the reference's operation order, so the winner is
+// the same point except for exact distance ties between points of different leaves.
+struct PackedNnScene {
+    float max_dist_sq;
+    const float4* nodes;      // 2 per node
+    const float4* pts4;       // {x, y, z, 0}
+    const float* nrm;         // original Vec3f normals
+    int n_nodes;
+    const unsigned* unsupported;   // device flag raised by nn_pack_nodes_kernel: this tree does not fit the encoding
+    NnScene ref;              // the reference layout (fallback walk when the stack would overflow)
+};
+
+__global__ void __launch_bounds__(256)
+nn_pack_points_kernel(const float* __restrict__ pcd, size_t n, float4* __restrict__ pts4) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) pts4[i] = make_float4(pcd[3 * i], pcd[3 * i + 1], pcd[3 * i + 2], 0.f);
+}
+// sets *unsupported when a leaf does not fit the packed encoding (more than 127 points or left >= 2^24)
+__global__ void __launch_bounds__(256)
+nn_pack_nodes_kernel(const pr_node_kdtree* __restrict__ nodes, int n_nodes, const float* __restrict__ pcd,
+                     float4* __restrict__ out, unsigned* __restrict__ unsupported) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_nodes) return;
+    const pr_node_kdtree nd = nodes[i];
+    float lo[3], hi[3];
+    int a;
+    if (nd.child1 < 0 || nd.child2 < 0) {
+        const int cnt = nd.right - nd.left;
+        if (cnt < 0 || cnt > 127 || nd.left < 0 || nd.left >= (1 << 24)) { *unsupported = 1; return; }
+        for (int k = 0; k < 3; k++) { lo[k] = FLT_MAX; hi[k] = -FLT_MAX; }
+        for (int j = nd.left; j < nd.right; j++)
+            for (int k = 0; k < 3; k++) { const float v = pcd[3 * j + k]; lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v); }
+        a = (int)(0x80000000u | ((unsigned)cnt << 24) | (unsigned)nd.left);
+    } else {
+        if (nd.child2 != nd.child1 + 1) { *unsupported = 1; return; }
+        for (int k = 0; k < 3; k++) { lo[k] = nd.bbox[2 * k]; hi[k] = nd.bbox[2 * k + 1]; }
+        a = nd.child1;
+    }
+    out[2 * i] = make_float4(lo[0], lo[1], lo[2], __int_as_float(a));
+    out[2 * i + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+}
+
+__device__ __forceinline__ float box_dist_sq(const float4& lo, const float4& hi, float px, float py, float pz) {
+    const float dx = fmaxf(fmaxf(lo.x - px, px - hi.x), 0.f);
+    const float dy = fmaxf(fmaxf(lo.y - py, py - hi.y), 0.f);
+    const float dz = fmaxf(fmaxf(lo.z - pz, pz - hi.z), 0.f);
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// exact nearest neighbour over the packed tree: index of the winner (leaf order), or -1 when nothing is nearer
+// than max_dist.  -2: the explicit stack overflowed (the caller falls back to the reference walk).
+__device__ __forceinline__ int nn_search_packed(const PackedNnScene& s, float px, float py, float pz) {
+    if (s.n_nodes <= 0) return -1;
+    constexpr int kStack = 24;       // far children parked: one per level at most (trees here are <= 20 deep)
+    int stack_n[kStack];
+    float stack_lb[kStack];
+    int sp = 0;
+    float best = s.max_dist_sq;
+    int best_i = -1;
+    bool overflow = false;
+    float4 lo = __ldg(s.nodes), hi = __ldg(s.nodes + 1);
+    // a box lower bound is rounded, so it is trusted only with a 1e-5 margin
+    bool go = box_dist_sq(lo, hi, px, py, pz) * 0.99999f < best;
+    while (go) {
+        const int a = __float_as_int(lo.w);
+        if (a < 0) {
+            const int left = a & 0xFFFFFF, cnt = (a >> 24) & 127;
+            for (int i = left; i < left + cnt; i++) {
+                const float4 q = __ldg(s.pts4 + i);
+                const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+                const float d2 = addf(addf(mulf(dx, dx), mulf(dy, dy)), mulf(dz, dz));    // pcd_scene.h:86-89
+                if (d2 < best) { best = d2; best_i = i; }
+            }
+            go = false;
+        } else {
+            const float4 lo1 = __ldg(s.nodes + 2 * a), hi1 = __ldg(s.nodes + 2 * a + 1);
+            const float4 lo2 = __ldg(s.nodes + 2 * a + 2), hi2 = __ldg(s.nodes + 2 * a + 3);
+            const float lb1 = box_dist_sq(lo1, hi1, px, py, pz) * 0.99999f, lb2 = box_dist_sq(lo2, hi2, px, py, pz) * 0.99999f;
+            const bool first1 = lb1 <= lb2;
+            const float lb_near = first1 ? lb1 : lb2, lb_far = first1 ? lb2 : lb1;
+            if (lb_far < best) {
+                if (sp < kStack) { stack_n[sp] = first1 ? a + 1 : a; stack_lb[sp] = lb_far; sp++; }
+                else overflow = true;
+            }
+            if (lb_near < best) { lo = first1 ? lo1 : lo2; hi = first1 ? hi1 : hi2; continue; }
+            go = false;
+        }
+        while (sp > 0) {
+            --sp;
+            if (stack_lb[sp] < best) {
+                const int n = stack_n[sp];
+                lo = __ldg(s.nodes + 2 * n); hi = __ldg(s.nodes + 2 * n + 1);
+                go = true;
+                break;
+            }
+        }
+    }
+    return overflow ? -2 : best_i;
+}
+
+__device__ __forceinline__ bool query(const PackedNnScene& s, float px, float py, float pz, Corr& c) {
+    if (s.nodes == nullptr) return query(s.ref, px, py, pz, c);
+    const int best_i = nn_search_packed(s, px, py, pz);
+    if (best_i == -2) return query(s.ref, px, py, pz, c);     // deeper than the stack: the reference walk
+    if (best_i < 0) return false;
+    const float4 q = __ldg(s.pts4 + best_i);
+    c.qx = q.x; c.qy = q.y; c.qz = q.z;
+    c.nx = __ldg(s.nrm + 3 * best_i); c.ny = __ldg(s.nrm + 3 * best_i + 1); c.nz = __ldg(s.nrm + 3 * best_i + 2);
+    return true;
+}
+
+// thrust__pcd2Ab::operator() (icp.h:138-208): adds one correspondence into the 29 running sums.
+__device__ __forceinline__ void accumulate(float* acc, float px, float py, float pz, const Corr& c, float w = 1.0f) {
+    const float dx = c.qx - px, dy = c.qy - py, dz = c.qz - pz;
+    const float r = dx * c.nx + dy * c.ny + dz * c.nz;
+    float J[6];
+    J[0] = c.nz * py - c.ny * pz;
+    J[1] = c.nx * pz - c.nz * px;
+    J[2] = c.ny * px - c.nx * py;
+    J[3] = c.nx; J[4] = c.ny; J[5] = c.nz;
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = i; j < 6; j++) { acc[k] = fmaf(J[i], J[j], acc[k]); k++; }
+#pragma unroll
+    for (int i = 0; i < 6; i++) acc[21 + i] = fmaf(J[i], r, acc[21 + i]);
+    acc[27] += dx * dx + dy * dy + dz * dz;
+    acc[28] += w;
+}
+
+// ---- packed accumulation (sm_100 FFMA2) ------------------------------------------------------------
+// Blackwell has a two-wide FP32 FMA (PTX fma.rn.f32x2, SASS FFMA2) whose first multiplicand may be a
+// scalar broadcast.  The 21 + 6 products J_i*J_j, J_i*r are rows "J_i x (J_i..J_5, r)", so with J and r
+// parked in the pairs E0=(J0,J1) E1=(J2,J3) E2=(J4,J5) E3=(r,0) they take 18 FFMA2 instead of 27 FFMA
+// (row 1, 3, 5 start on an odd element: that lane recomputes the symmetric product and is ignored).
+struct Acc2 {
+    float2 p[18];      // see unpack_acc2 for the slot -> Vec29f index map
+    float2 dd;         // sum dx^2, sum dy^2
+    float dz2, cnt;
+};
+__device__ __forceinline__ float2 ffma2(float a, float2 b, float2 c) {     // a * b + c, a broadcast
+    float2 d;
+    asm("{\n"
+        ".reg .b64 ra, rb, rc, rd;\n"
+        "mov.b64 ra, {%2, %2};\n"
+        "mov.b64 rb, {%3, %4};\n"
+        "mov.b64 rc, {%5, %6};\n"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n"
+        "mov.b64 {%0, %1}, rd;\n"
+        "}\n" : "=f"(d.x), "=f"(d.y) : "f"(a), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 ffma2v(float2 a, float2 b, float2 c) {   // element-wise a * b + c
+    float2 d;
+    asm("{\n"
+        ".reg .b64 ra, rb, rc, rd;\n"
+        "mov.b64 ra, {%2, %3};\n"
+        "mov.b64 rb, {%4, %5};\n"
+        "mov.b64 rc, {%6, %7};\n"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n"
+        "mov.b64 {%0, %1}, rd;\n"
+        "}\n" : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ void zero_acc2(Acc2& a) {
+#pragma unroll
+    for (int i = 0; i < 18; i++) a.p[i] = make_float2(0.f, 0.f);
+    a.dd = make_float2(0.f, 0.f); a.dz2 = 0.f; a.cnt = 0.f;
+}
+__device__ __forceinline__ void accumulate2(Acc2& a, float px, float py, float pz, const Corr& c, float w = 1.0f) {
+    const float dx = c.qx - px, dy = c.qy - py, dz = c.qz - pz;
+    const float r = dx * c.nx + dy * c.ny + dz * c.nz;
+    const float2 E0 = make_float2(c.nz * py - c.ny * pz, c.nx * pz - c.nz * px);
+    const float2 E1 = make_float2(c.ny * px - c.nx * py, c.nx);
+    const float2 E2 = make_float2(c.ny, c.nz);
+    const float2 E3 = make_float2(r, 0.f);
+    a.p[0] = ffma2(E0.x, E0, a.p[0]); a.p[1] = ffma2(E0.x, E1, a.p[1]); a.p[2] = ffma2(E0.x, E2, a.p[2]); a.p[3] = ffma2(E0.x, E3, a.p[3]);
+    a.p[4] = ffma2(E0.y, E0, a.p[4]); a.p[5] = ffma2(E0.y, E1, a.p[5]); a.p[6] = ffma2(E0.y, E2, a.p[6]); a.p[7] = ffma2(E0.y, E3, a.p[7]);
+    a.p[8] = ffma2(E1.x, E1, a.p[8]); a.p[9] = ffma2(E1.x, E2, a.p[9]); a.p[10] = ffma2(E1.x, E3, a.p[10]);
+    a.p[11] = ffma2(E1.y, E1, a.p[11]); a.p[12] = ffma2(E1.y, E2, a.p[12]); a.p[13] = ffma2(E1.y, E3, a.p[13]);
+    a.p[14] = ffma2(E2.x, E2, a.p[14]); a.p[15] = ffma2(E2.x, E3, a.p[15]);
+    a.p[16] = ffma2(E2.y, E2, a.p[16]); a.p[17] = ffma2(E2.y, E3, a.p[17]);
+    a.dd = ffma2v(make_float2(dx, dy), make_float2(dx, dy), a.dd);
+    a.dz2 = fmaf(dz, dz, a.dz2);
+    a.cnt += w;
+}
+// packed slots -> the 29 sums in thrust__pcd2Ab's order (icp.h:165-206), padded to 32
+__device__ __forceinline__ void unpack_acc2(const Acc2& a, float (&v)[32]) {
+    v[0] = a.p[0].x;  v[1] = a.p[0].y;  v[2] = a.p[1].x;  v[3] = a.p[1].y;  v[4] = a.p[2].x;  v[5] = a.p[2].y;   // J0 * J0..J5
+    v[6] = a.p[4].y;  v[7] = a.p[5].x;  v[8] = a.p[5].y;  v[9] = a.p[6].x;  v[10] = a.p[6].y;                    // J1 * J1..J5
+    v[11] = a.p[8].x; v[12] = a.p[8].y; v[13] = a.p[9].x; v[14] = a.p[9].y;                                      // J2 * J2..J5
+    v[15] = a.p[11].y; v[16] = a.p[12].x; v[17] = a.p[12].y;                                                     // J3 * J3..J5
+    v[18] = a.p[14].x; v[19] = a.p[14].y;                                                                        // J4 * J4..J5
+    v[20] = a.p[16].y;                                                                                           // J5 * J5
+    v[21] = a.p[3].x; v[22] = a.p[7].x; v[23] = a.p[10].x; v[24] = a.p[13].x; v[25] = a.p[15].x; v[26] = a.p[17].x;   // J * r
+    v[27] = a.dd.x + a.dd.y + a.dz2;
+    v[28] = a.cnt;
+    v[29] = 0.f; v[30] = 0.f; v[31] = 0.f;
+}
+
+
+// ---- two points per instruction ---------------------------------------------------------------------
+// The second generation of the packed path: instead of packing two SUMS of one point into an FFMA2
+// (which needs register moves to form the operand pairs), every quantity of the point pipeline is a
+// pair (value for point A, value for point B) of the two points a lane processes together --
+// transform, projection, residual, Jacobian and all 29 sums run as FFMA2 / FMUL2 / FADD2 with no
+// packing moves: the per-point selects that reject a correspondence write straight into the halves of
+// the pair registers.  Sum i is kept as (sum over "A" points, sum over "B" points) and folded at the end
+// of the item.  Pairs are carried as 64-bit values so that ptxas allocates them as aligned register
+// pairs once; it folds negation and scalar broadcast into the FFMA2 operands.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk2(float lo, float hi) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2_t bc2(float a) { return pk2(a, a); }
+__device__ __forceinline__ void unpk2(f2_t a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); }
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) { f2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+// acc += a * b with the accumulator as a read-write operand: input and output are the same register pair by
+// construction, so ptxas has no loop-carried copies to insert at the back edge of the group loop
+__device__ __forceinline__ void fma2_acc(f2_t& acc, f2_t a, f2_t b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) { f2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2_t add2(f2_t a, f2_t b) { f2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2_t sub2(f2_t a, f2_t b) { f2_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2_t neg2(f2_t a) {
+    f2_t d;
+    asm("{\n.reg .f32 l, h;\nmov.b64 {l, h}, %1;\nneg.f32 l, l;\nneg.f32 h, h;\nmov.b64 %0, {l, h};\n}" : "=l"(d) : "l"(a));
+    return d;
+}
+// s[i] = Vec29f entry i (icp.h:165-206) as (sum over A points, sum over B points); the inlier count is an integer
+// (a predicated IADD runs on the ALU pipe, the FP32 pipe is the one this kernel saturates)
+struct AccP { f2_t s[28]; int cnt; };
+__device__ __forceinline__ void acc_zero(AccP& a) {
+#pragma unroll
+    for (int i = 0; i < 28; i++) a.s[i] = pk2(0.f, 0.f);
+    a.cnt = 0;
+}
+__device__ __forceinline__ void acc_unpack(const AccP& a, float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 28; i++) { float lo, hi; unpk2(a.s[i], lo, hi); v[i] = lo + hi; }
+    v[28] = (float)a.cnt;
+    v[29] = 0.f; v[30] = 0.f; v[31] = 0.f;
+}
+// thrust__pcd2Ab::operator() (icp.h:138-208) for two points at once; a rejected point arrives as q = p, n = 0
+// (so d = 0, r = 0, J = 0: all 28 float sums get +0); the caller counts the accepted points.
+__device__ __forceinline__ void accumulate_pair(AccP& a, f2_t px, f2_t py, f2_t pz, f2_t qx, f2_t qy, f2_t qz,
+                                                f2_t nx, f2_t ny, f2_t nz) {
+    const f2_t dx = sub2(qx, px), dy = sub2(qy, py), dz = sub2(qz, pz);
+    const f2_t r = fma2(dz, nz, fma2(dy, ny, mul2(dx, nx)));
+    f2_t J[6];
+    J[0] = fma2(nz, py, neg2(mul2(ny, pz)));
+    J[1] = fma2(nx, pz, neg2(mul2(nz, px)));
+    J[2] = fma2(ny, px, neg2(mul2(nx, py)));
+    J[3] = nx; J[4] = ny; J[5] = nz;
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = i; j < 6; j++) { fma2_acc(a.s[k], J[i], J[j]); k++; }
+#pragma unroll
+    for (int i = 0; i < 6; i++) fma2_acc(a.s[21 + i], J[i], r);
+    fma2_acc(a.s[27], dx, dx); fma2_acc(a.s[27], dy, dy); fma2_acc(a.s[27], dz, dz);
+}
+
+__device__ __forceinline__ void acc_zero(Acc2& a) { zero_acc2(a); }
+__device__ __forceinline__ void acc_add(Acc2& a, float px, float py, float pz, const Corr& c) { accumulate2(a, px, py, pz, c); }
+__device__ __forceinline__ void acc_unpack(const Acc2& a, float (&v)[32]) { unpack_acc2(a, v); }
+typedef Acc2 AccT;     // per-point accumulation of the nearest-neighbour scenes; the projective driver uses AccP
+
+// Warp reduction of 32 values per lane that leaves, in lane L, the warp-wide sum of value L:
+// at each butterfly step a lane keeps one half of its values and ships the other half, so the
+// whole thing costs 16+8+4+2+1 = 31 shuffles instead of 32*5.
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32]) {
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; i++) {
+            const float send = upper ? v[i] : v[i + off];
+            const float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+}  // namespace prb

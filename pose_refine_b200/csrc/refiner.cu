@@ -37,6 +37,10 @@ struct pr_refiner {
     float* d_scene_pcd = nullptr;
     float* d_scene_nrm = nullptr;
     pr_node_kdtree* d_nodes = nullptr;
+    void* d_scene_packed = nullptr;   // 32-byte records of the projective scene, packed once per scene
+    void* d_scene_depth = nullptr;    // staging for a host depth image (4 bytes per pixel)
+    void* d_scene_ws = nullptr;       // kd-tree build workspace
+    size_t scene_ws_bytes = 0;
     pr_scene_projective sp;
     pr_scene_nn sn;
     uint32_t* h_overflow = nullptr;   // pinned
@@ -46,8 +50,16 @@ namespace {
 
 void free_scene(pr_refiner* r) {
     cudaFree(r->d_scene_pcd); cudaFree(r->d_scene_nrm); cudaFree(r->d_nodes);
+    cudaFree(r->d_scene_packed); cudaFree(r->d_scene_depth); cudaFree(r->d_scene_ws);
     r->d_scene_pcd = nullptr; r->d_scene_nrm = nullptr; r->d_nodes = nullptr;
+    r->d_scene_packed = nullptr; r->d_scene_depth = nullptr; r->d_scene_ws = nullptr;
     r->scene_kind = -1;
+}
+// scene buffers are allocated on first use and kept: setting a scene never allocates after that
+int ensure(void** p, size_t bytes) {
+    if (*p) return PR_OK;
+    PR_CUDA_TRY(cudaMalloc(p, bytes ? bytes : 256));
+    return PR_OK;
 }
 
 int run_device(pr_refiner* r, const float* poses_dev, size_t n_hyp, pr_icp_criteria crit,
@@ -59,8 +71,8 @@ int run_device(pr_refiner* r, const float* poses_dev, size_t n_hyp, pr_icp_crite
                                    &r->clusters, r->ws_render, r->ws_render_bytes, s);
     if (rc != PR_OK) return rc;
     if (r->scene_kind == 0)
-        return pr_icp_projective_batch(r->d_pts, r->d_offsets, r->d_counts, n_hyp, r->capacity_points, &r->sp, crit, results_dev, 0,
-                                       r->ws_icp, r->ws_icp_bytes, s);
+        return pr_icp_projective_batch_packed(r->d_pts, r->d_offsets, r->d_counts, n_hyp, r->capacity_points, &r->sp, r->d_scene_packed,
+                                              crit, results_dev, 0, r->ws_icp, r->ws_icp_bytes, s);
     return pr_icp_nn_batch(r->d_pts, r->d_offsets, r->d_counts, n_hyp, r->capacity_points, &r->sn, crit, results_dev, 0,
                            r->ws_icp, r->ws_icp_bytes, s);
 }
@@ -80,6 +92,7 @@ const char* pr_error_string(int status) {
     case PR_ERR_CAPACITY: return "output capacity exceeded";
     case PR_ERR_IO: return "i/o error";
     case PR_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+    case PR_ERR_COMM: return "NCCL unavailable or an NCCL call failed";
     }
     if (status > 0) return cudaGetErrorString((cudaError_t)status);
     return "unknown error";
@@ -184,52 +197,67 @@ void pr_refiner_destroy(pr_refiner* r) {
     delete r;
 }
 
-int pr_refiner_set_scene_projective(pr_refiner* r, const void* depth_host, int depth_is_int32, float max_dist_diff) {
-    if (!r || !depth_host) return PR_ERR_INVALID_ARGUMENT;
-    free_scene(r);
+int pr_refiner_set_scene_projective_device(pr_refiner* r, const void* depth_dev, int depth_is_int32, float max_dist_diff,
+                                           pr_stream_t stream) {
+    if (!r || !depth_dev) return PR_ERR_INVALID_ARGUMENT;
     const size_t n_px = (size_t)r->W * r->H;
-    void* d_depth = nullptr;
-    PR_CUDA_TRY(cudaMalloc(&d_depth, n_px * (depth_is_int32 ? 4 : 2)));
-    cudaError_t e = cudaMalloc((void**)&r->d_scene_pcd, n_px * 12);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_scene_nrm, n_px * 12);
-    if (e == cudaSuccess) e = cudaMemcpy(d_depth, depth_host, n_px * (depth_is_int32 ? 4 : 2), cudaMemcpyHostToDevice);
-    int rc = (e == cudaSuccess) ? pr_scene_projective_init(d_depth, depth_is_int32, r->W, r->H, r->K, r->d_scene_pcd, r->d_scene_nrm, 0) : (int)e;
-    if (rc == PR_OK) { e = cudaDeviceSynchronize(); rc = (e == cudaSuccess) ? PR_OK : (int)e; }
-    cudaFree(d_depth);
-    if (rc != PR_OK) { free_scene(r); return rc; }
+    int rc = ensure((void**)&r->d_scene_pcd, n_px * 12 + 256);
+    if (rc == PR_OK) rc = ensure((void**)&r->d_scene_nrm, n_px * 12 + 256);
+    if (rc == PR_OK) rc = ensure(&r->d_scene_packed, n_px * 32);
+    if (rc != PR_OK) return rc;
+    r->scene_kind = -1;
+    rc = pr_scene_projective_init(depth_dev, depth_is_int32, r->W, r->H, r->K, r->d_scene_pcd, r->d_scene_nrm, stream);
+    if (rc != PR_OK) return rc;
     r->sp.width = r->W; r->sp.height = r->H; r->sp.max_dist_diff = max_dist_diff;
     memcpy(r->sp.K, r->K, 36);
     r->sp.pcd_dev = r->d_scene_pcd; r->sp.normal_dev = r->d_scene_nrm;
+    rc = pr_scene_projective_pack(&r->sp, r->d_scene_packed, stream);
+    if (rc != PR_OK) return rc;
     r->scene_kind = 0;
     return PR_OK;
 }
 
-int pr_refiner_set_scene_nn(pr_refiner* r, const void* depth_host, int depth_is_int32) {
+int pr_refiner_set_scene_projective(pr_refiner* r, const void* depth_host, int depth_is_int32, float max_dist_diff) {
     if (!r || !depth_host) return PR_ERR_INVALID_ARGUMENT;
-    free_scene(r);
     const size_t n_px = (size_t)r->W * r->H;
-    const size_t px_bytes = depth_is_int32 ? 4 : 2;
-    // upload the image and build everything on the device (pr_scene_nn_build): points, normals, kd-tree
-    void *d_depth = nullptr, *d_ws = nullptr;
-    const size_t ws_bytes = pr_scene_nn_build_workspace_bytes(r->W, r->H);
+    int rc = ensure(&r->d_scene_depth, n_px * 4);
+    if (rc != PR_OK) return rc;
+    PR_CUDA_TRY(cudaMemcpy(r->d_scene_depth, depth_host, n_px * (depth_is_int32 ? 4 : 2), cudaMemcpyHostToDevice));
+    rc = pr_refiner_set_scene_projective_device(r, r->d_scene_depth, depth_is_int32, max_dist_diff, nullptr);
+    if (rc != PR_OK) return rc;
+    PR_CUDA_TRY(cudaStreamSynchronize(nullptr));
+    return PR_OK;
+}
+
+int pr_refiner_set_scene_nn_device(pr_refiner* r, const void* depth_dev, int depth_is_int32, pr_stream_t stream) {
+    if (!r || !depth_dev) return PR_ERR_INVALID_ARGUMENT;
+    const size_t n_px = (size_t)r->W * r->H;
+    // everything is built on the device (pr_scene_nn_build): points, normals, kd-tree
+    r->scene_ws_bytes = pr_scene_nn_build_workspace_bytes(r->W, r->H);
+    int rc = ensure(&r->d_scene_ws, r->scene_ws_bytes);
+    if (rc == PR_OK) rc = ensure((void**)&r->d_scene_pcd, n_px * 12 + 256);
+    if (rc == PR_OK) rc = ensure((void**)&r->d_scene_nrm, n_px * 12 + 256);
+    if (rc == PR_OK) rc = ensure((void**)&r->d_nodes, (2 * n_px + 1) * sizeof(pr_node_kdtree));
+    if (rc != PR_OK) return rc;
+    r->scene_kind = -1;
     size_t n_pts = 0, n_nodes = 0;
-    cudaError_t e = cudaMalloc(&d_depth, n_px * px_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&d_ws, ws_bytes);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_scene_pcd, n_px * 12 + 256);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_scene_nrm, n_px * 12 + 256);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_nodes, (2 * n_px + 1) * sizeof(pr_node_kdtree));
-    if (e == cudaSuccess) e = cudaMemcpy(d_depth, depth_host, n_px * px_bytes, cudaMemcpyHostToDevice);
-    int rc = (e == cudaSuccess) ? PR_OK : (int)e;
-    if (rc == PR_OK)
-        rc = pr_scene_nn_build(d_depth, depth_is_int32, r->W, r->H, r->K, 10, r->d_scene_pcd, r->d_scene_nrm, n_px, r->d_nodes,
-                               2 * n_px + 1, &n_pts, &n_nodes, d_ws, ws_bytes, nullptr);
-    cudaFree(d_depth); cudaFree(d_ws);
-    if (rc != PR_OK) { free_scene(r); return rc; }
+    rc = pr_scene_nn_build(depth_dev, depth_is_int32, r->W, r->H, r->K, 10, r->d_scene_pcd, r->d_scene_nrm, n_px, r->d_nodes,
+                           2 * n_px + 1, &n_pts, &n_nodes, r->d_scene_ws, r->scene_ws_bytes, stream);
+    if (rc != PR_OK) return rc;
     r->sn.max_dist_diff = 0.1f;   // Scene_nn has no setter upstream (pcd_scene.h:49)
     r->sn.pcd_dev = r->d_scene_pcd; r->sn.normal_dev = r->d_scene_nrm; r->sn.nodes_dev = r->d_nodes;
     r->sn.n_points = n_pts; r->sn.n_nodes = n_nodes;
     r->scene_kind = 1;
     return PR_OK;
+}
+
+int pr_refiner_set_scene_nn(pr_refiner* r, const void* depth_host, int depth_is_int32) {
+    if (!r || !depth_host) return PR_ERR_INVALID_ARGUMENT;
+    const size_t n_px = (size_t)r->W * r->H;
+    int rc = ensure(&r->d_scene_depth, n_px * 4);
+    if (rc != PR_OK) return rc;
+    PR_CUDA_TRY(cudaMemcpy(r->d_scene_depth, depth_host, n_px * (depth_is_int32 ? 4 : 2), cudaMemcpyHostToDevice));
+    return pr_refiner_set_scene_nn_device(r, r->d_scene_depth, depth_is_int32, nullptr);
 }
 
 int pr_refiner_run_device(pr_refiner* r, const float* poses_dev, size_t n_hyp, pr_icp_criteria criteria,

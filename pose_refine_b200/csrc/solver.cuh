@@ -175,4 +175,68 @@ __host__ __device__ __forceinline__ void solve_666_unrolled(const float (&S)[29]
     pose_from_x(x, E);
 }
 
+// ---- the solver the hypothesis-resident ICP kernel runs between two passes ---------------------------
+// The pass-to-pass chain of a hypothesis is serial (sums -> solve -> new 4x4 -> next pass), so what counts here
+// is the LATENCY of one solve on one thread.  solve_666_unrolled reproduces Eigen's pivoted LDL^T operation for
+// operation: 21 IEEE double divisions, each a call-sized sequence (~7 us per solve on a B200 thread).  (A + 0.01 I)
+// is symmetric positive definite (A is a sum of J J^T), so LDL^T needs no pivoting for stability; this variant
+// factors without it and multiplies by one reciprocal per column (hardware seed + three Newton steps).  The
+// critical path is ~200 dependent double operations instead of ~1500.  The solution x differs from the pivoted
+// one by O(cond * 1e-16), i.e. not at all after the cast to float except for an occasional last-bit flip
+// (tests/test_gpu_parity.py::test_fast_solver_matches_exact pins the difference).
+#ifdef __CUDACC__
+__device__ __forceinline__ double rcp_newton(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));       // ~2^-23 relative
+    double e = fma(-d, r, 1.0); r = fma(r, e, r);                // 2^-46
+    e = fma(-d, r, 1.0); r = fma(r, e, r);                       // 2^-92 -> limited by double rounding
+    e = fma(-d, r, 1.0); r = fma(r, e, r);                       // absorbs the rounding of the previous step
+    return r;
+}
+__device__ __forceinline__ void solve_666_fast(const float (&S)[29], float (&E)[16]) {
+    double a[6][6], x[6], dinv[6];
+    {
+        int shift = 0;
+#pragma unroll
+        for (int y = 0; y < 6; y++)
+#pragma unroll
+            for (int xx = y; xx < 6; xx++) a[xx][y] = (double)S[shift++] + (xx == y ? 0.01 : 0.0);   // lower triangle, icp.cu:198-205
+#pragma unroll
+        for (int i = 0; i < 6; i++) x[i] = (double)S[21 + i];
+    }
+    // A = L D L^T, L unit lower (stored in a[i][j], i > j), D in a[j][j]
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        double v[6];
+#pragma unroll
+        for (int k = 0; k < j; k++) v[k] = a[j][k] * a[k][k];
+        double d = a[j][j];
+#pragma unroll
+        for (int k = 0; k < j; k++) d = fma(-a[j][k], v[k], d);
+        a[j][j] = d;
+        dinv[j] = rcp_newton(d);
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+            double s = a[i][j];
+#pragma unroll
+            for (int k = 0; k < j; k++) s = fma(-a[i][k], v[k], s);
+            a[i][j] = s * dinv[j];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+#pragma unroll
+        for (int j = 0; j < i; j++) x[i] = fma(-a[i][j], x[j], x[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) x[i] *= dinv[i];
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+#pragma unroll
+        for (int j = i + 1; j < 6; j++) x[i] = fma(-a[j][i], x[j], x[i]);
+    }
+    pose_from_x(x, E);
+}
+#endif
+
 }  // namespace prb

@@ -338,6 +338,130 @@ def test_pcd2ab_matches_oracle(api, port, fixture_scene, golden):
         assert np.all(np.abs(arrays[key].astype(np.float64) - truth) <= 2e-5 * mag), "golden CPU sums are themselves only this close"
 
 
+def _hyp8_clouds(api, mesh, arrays):
+    depth = api.render_cuda_keep_in_gpu(mesh, arrays["hyp8"], 640, 480, arrays["proj"])
+    return api.depth2cloud_batch(depth, arrays["K"])
+
+
+def test_pass_sums_of_the_shipped_kernel(api, port, mesh, fixture_scene, golden, torch_mod):
+    """The same bar as test_pcd2ab_matches_oracle, for the kernel pr_icp_*_batch actually runs (icp_hyp_kernel): one
+    evaluation pass over the fixture cloud and over the 8 clouds of the golden batch, both scene types --
+    inlier count exact, every sum within 2e-6 of sum|term| of the float64 sum over the ORACLE's correspondences."""
+    arrays, _ = golden
+    K = arrays["K"]
+    pts, offsets, counts = _hyp8_clouds(api, mesh, arrays)
+    h_pts, h_off, h_cnt = pts.cpu().numpy(), offsets.cpu().numpy(), counts.cpu().numpy()
+    clouds = [fixture_scene["cloud"]] + [h_pts[h_off[i]: h_off[i] + h_cnt[i]] for i in range(8)]
+    cat = np.concatenate(clouds)
+    off = np.cumsum([0] + [len(c) for c in clouds]).astype(np.int32)
+    d_pts, d_off = torch_mod.as_tensor(cat).cuda(), torch_mod.as_tensor(off[:-1]).cuda()
+    d_cnt = torch_mod.as_tensor(np.array([len(c) for c in clouds], np.int32)).cuda()
+    for scene, pscene in ((api.SceneProjective().init_cuda(fixture_scene["scene_depth"], K), port.scene_projective(fixture_scene["scene_depth"], K)),
+                          (api.SceneNN().init_cuda(fixture_scene["scene_depth"], K), port.scene_nn(fixture_scene["scene_depth"], K))):
+        got = api.pass_sums(d_pts, d_off, d_cnt, scene).astype(np.float64)
+        for i, cloud in enumerate(clouds):
+            q, n, valid = port.query(pscene, cloud)
+            terms = _terms_f64(cloud, q, n, valid)
+            truth, mag = terms.sum(0), np.abs(terms).sum(0)
+            assert got[i, 28] == truth[28], f"cloud {i}: inlier count {got[i, 28]} vs {truth[28]}"
+            assert np.all(np.abs(got[i] - truth) <= 2e-6 * mag + 1e-30), (i, (got[i] - truth) / np.maximum(mag, 1e-30))
+
+
+def _moved(cloud, seed):
+    """the cloud under a small rigid motion, computed in float32 on the host (what an ICP pass would look at)"""
+    rng = np.random.RandomState(seed)
+    R = wl.euler_zyx(np.deg2rad(rng.uniform(-4, 4, 3)))
+    t = rng.uniform(-0.01, 0.01, 3).astype(np.float32)
+    return (cloud @ R.T + t).astype(np.float32)
+
+
+def test_correspondences_projective_match_the_oracle_point_by_point(api, port, mesh, fixture_scene, golden):
+    """Pixel selection of the hot loop (project_pair / pixel_of + depth gate) against Scene_projective::query
+    (depth_scene.h:30-48, pcd2dep common.h:63-73) for EVERY point of 9 clouds, each as rendered and under three small
+    motions, plus points engineered onto the image border, behind the camera and non-finite.  Pinned: 0 mismatches."""
+    arrays, _ = golden
+    K = arrays["K"]
+    sp = api.SceneProjective().init_cuda(fixture_scene["scene_depth"], K)
+    ps = port.scene_projective(fixture_scene["scene_depth"], K)
+    scene_pcd = sp.pcd.cpu().numpy()
+    pts, offsets, counts = _hyp8_clouds(api, mesh, arrays)
+    h_pts, h_off, h_cnt = pts.cpu().numpy(), offsets.cpu().numpy(), counts.cpu().numpy()
+    clouds = [fixture_scene["cloud"]] + [h_pts[h_off[i]: h_off[i] + h_cnt[i]] for i in range(8)]
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    z = np.float32(0.3)
+    edge = []
+    for u in (-1.5, -1.0, -0.75, -0.5, -0.25, 0.0, 0.49, 319.5, 638.5, 639.0, 639.49, 639.5, 640.0):
+        for v in (-1.0, -0.5, 0.0, 240.0, 479.0, 479.49, 479.5, 480.0):
+            edge.append([(np.float32(u) - cx) / fx * z, (np.float32(v) - cy) / fy * z, z])
+    edge += [[0, 0, -0.3], [0, 0, 0], [np.nan, 0, 0.3], [0, np.inf, 0.3], [0.01, 0.01, np.nan], [1e30, 0, 0.3], [0, 0, 1e-30], [1e-20, 1e-20, 1e-19]]
+    clouds.append(np.asarray(edge, np.float32))
+    total = mismatches = inliers = 0
+    for ci, cloud in enumerate(clouds):
+        for variant in range(4):
+            c = cloud if variant == 0 else _moved(cloud, 100 * ci + variant)
+            idx = api.correspondences(c, sp)
+            q, n, valid = port.query(ps, c)
+            bad = (idx >= 0) != valid
+            both = (idx >= 0) & valid
+            bad[both] |= np.any(scene_pcd[idx[both]] != q[both], axis=1)
+            total += len(c); mismatches += int(bad.sum()); inliers += int(valid.sum())
+    print(f"projective correspondences: {mismatches} mismatches in {total} points ({inliers} inliers)")
+    assert inliers > 0.5 * total
+    assert mismatches == 0
+
+
+def test_fast_solver_matches_exact(api, port, fixture_scene, golden):
+    """The solver the kernel runs between passes (unpivoted LDL^T with Newton reciprocals, solver.cuh) against the
+    restatement of Eigen's pivoted LDL^T on the device and the oracle's on the host: 300 random well-posed systems
+    plus the fixture's own first-pass system; the float 4x4 may differ in the last bit only."""
+    arrays, _ = golden
+    rng = np.random.RandomState(7)
+    S = np.zeros((301, 29), np.float32)
+    for i in range(300):
+        J = rng.normal(size=(400, 6)) * np.array([0.3, 0.3, 0.3, 1, 1, 1])
+        r = rng.normal(size=400) * 0.01
+        A, b = J.T @ J, J.T @ r
+        k = 0
+        for y in range(6):
+            for x in range(y, 6):
+                S[i, k] = A[x, y]; k += 1
+        S[i, 21:27] = b
+    S[300] = arrays["pcd2ab_projective"]
+    fast = api.solve_666_device(S, fast=True)
+    exact = api.solve_666_device(S, fast=False)
+    for i in range(301):
+        A = np.zeros((6, 6), np.float32)
+        k = 0
+        for y in range(6):
+            for x in range(y, 6):
+                A[x, y] = A[y, x] = S[i, k]; k += 1
+        want = port.solve_666(A, S[i, 21:27])
+        assert np.array_equal(exact[i], want), f"system {i}: device restatement of the pivoted solver differs from the oracle"
+        ulp = np.spacing(np.abs(want).astype(np.float32)).astype(np.float64)
+        assert np.all(np.abs(fast[i].astype(np.float64) - want) <= 1.01 * ulp + 1e-12), (i, fast[i] - want)
+    print("fast vs exact solver: entries differing in the last bit:", int((fast != exact).sum()), "of", fast.size)
+
+
+def test_reference_arithmetic_driver_agrees(api, mesh, fixture_scene, golden):
+    """PR_ICP_REFERENCE_ARITHMETIC (one launch per pass, the reference's operation order, its kd-tree walk, the pivoted
+    solver) and the shipped kernel give the same poses on the golden batch, both scene types."""
+    arrays, _ = golden
+    K = arrays["K"]
+    pts, offsets, counts = _hyp8_clouds(api, mesh, arrays)
+    crit = api.ICPConvergenceCriteria(0.0, 0.0, 30)
+    sp = api.SceneProjective().init_cuda(fixture_scene["scene_depth"], K)
+    a = api.icp_batch(pts, offsets, counts, sp, crit).cpu().numpy()
+    b = api.icp_batch(pts, offsets, counts, sp, crit, reference_arithmetic=True).cpu().numpy()
+    for i in range(8):
+        assert_result_close(a[i], b[i], f"projective hyp {i}")
+        assert_result_close(b[i], arrays["icp_hyp8_projective_fixed30"][i], f"reference-arithmetic driver vs golden, hyp {i}")
+    sn = api.SceneNN().init_cuda(fixture_scene["scene_depth"], K)
+    a = api.icp_batch(pts[: int(offsets[2])], offsets[:2], counts[:2], sn, crit).cpu().numpy()
+    b = api.icp_batch(pts[: int(offsets[2])], offsets[:2], counts[:2], sn, crit, reference_arithmetic=True).cpu().numpy()
+    for i in range(2):
+        assert_result_close(a[i], b[i], f"nn hyp {i}")
+
+
 def test_icp_projective_fixture(api, port, fixture_scene, golden, torch_mod):
     arrays, _ = golden
     K = arrays["K"]
@@ -472,26 +596,33 @@ def test_full_size_properties(api, port, mesh, fixture_scene, golden, torch_mod)
     R = r[:, :16].reshape(P, 4, 4)[:, :3, :3].astype(np.float64)
     assert np.abs(R @ R.transpose(0, 2, 1) - np.eye(3)).max() < 1e-4, "accumulated updates stay rotations"
     assert np.isfinite(r).all() and (r[:, 17] >= 0).all() and (r[:, 17] <= 1).all() and (r[:, 17] > 0.5).mean() > 0.7
-    # spot-check hypotheses against the oracle end to end.  ICP on a poor hypothesis is chaotic: the
-    # reference's own CPU code run with a different thread count (= another float summation order)
-    # moves the final pose of a NON-converging hypothesis by O(1) and of a converging one by up to
-    # ~6e-5 (measured on this batch).  So each sampled hypothesis is held to
-    #     max(1e-4, 3 x the oracle's own spread over thread counts 1/2/5/8),
-    # and at least half of the sample must be reproducible (spread <= 3e-5) so the check is not vacuous.
-    ps = port.scene_projective(fixture_scene["scene_depth"], K)
-    sample = list(range(0, P, 32))
-    reproducible = 0
-    for i in sample:
-        d = port.render(mesh, poses[i: i + 1], 640, 480, arrays["proj"])[0]
-        assert np.array_equal(a[i].cpu().numpy(), d)
-        cloud = port.depth2cloud(d, K)
-        runs = []
-        for nt in (1, 2, 5, 8):
-            port.set_threads(nt)
-            runs.append(port.icp(ps, cloud, 0.0, 0.0, 30)["raw"][:16].astype(np.float64))
-        port.set_threads(1)
-        spread = max(np.abs(runs[0] - x).max() for x in runs[1:])
-        reproducible += spread <= 3e-5
-        err = np.abs(r[i, :16] - runs[0]).max()
-        assert err <= max(REL_TOL, 3 * spread), f"hyp {i}: |T_gpu - T_oracle| = {err:.2e}, oracle's own spread {spread:.2e}"
-    assert reproducible >= 0.5 * len(sample), f"only {reproducible}/{len(sample)} sampled hypotheses are reproducible"
+    # ---- every hypothesis against the oracle, end to end (tests/golden/c2_oracle_512.npz, scripts/make_golden_c2.py).
+    # ICP on a poor hypothesis is chaotic: the reference's own CPU code run with another OpenMP thread count (= another
+    # float summation order, nothing else) moves the final pose of a non-converging hypothesis by O(1) and of a
+    # converging one by up to ~1e-4.  The golden file holds the oracle's results for 1 / 2 / 5 / 8 threads; a
+    # hypothesis is REPRODUCIBLE when those four agree to 3e-5.  Bars: every reproducible hypothesis within
+    # max(1e-4, 3 x its own spread) -- north_star's tolerance -- and the count beyond a plain 1e-4 is printed.
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "c2_oracle_512.npz"))
+    want = g["results"].astype(np.float64)              # [4 thread counts, 512, 18]
+    assert np.array_equal(g["n_pts"], counts.cpu().numpy()), "cloud sizes equal the oracle's for all 512 hypotheses"
+    spread = np.abs(want[1:, :, :16] - want[0, :, :16]).max(axis=(0, 2))
+    err = np.abs(r[:, :16].astype(np.float64) - want[0, :, :16]).max(axis=1)
+    err_best = np.abs(r[None, :, :16].astype(np.float64) - want[:, :, :16]).max(axis=2).min(axis=0)
+    scale = np.abs(want[0, :, :16]).max(axis=1)         # = 1 (rotation entries / the homogeneous 1)
+    reproducible = spread <= 3e-5
+    converging = want[0, :, 17] > 0.9
+    beyond = err > REL_TOL * scale
+    print(f"C2 full size: {int(reproducible.sum())} of {P} hypotheses reproducible on the CPU itself, {int(converging.sum())} converging; "
+          f"beyond 1e-4 of the 1-thread oracle: {int((beyond & reproducible).sum())} of {int(reproducible.sum())} reproducible, "
+          f"{int((beyond & converging).sum())} of {int(converging.sum())} converging "
+          f"(the oracle's own 8-thread run: {int(((spread > 1e-4) & converging).sum())}); median err {np.median(err[reproducible]):.2e}, "
+          f"max err over reproducible {err[reproducible].max():.2e}")
+    assert reproducible.sum() >= 0.7 * P
+    bad = reproducible & (err_best > np.maximum(REL_TOL * scale, 3 * spread))
+    assert not bad.any(), f"hypotheses {np.nonzero(bad)[0][:10]}: err {err_best[bad][:10]}, oracle spread {spread[bad][:10]}"
+    # the statistics of the reproducible ones follow
+    ok = reproducible & ~beyond
+    assert np.all(np.abs(r[ok, 17] - want[0, ok, 17]) <= STAT_TOL * np.maximum(want[0, ok, 17], 1e-12))
+    assert np.all(np.abs(r[ok, 16] - want[0, ok, 16]) <= STAT_TOL * np.maximum(want[0, ok, 16], 1e-12))
