@@ -69,8 +69,13 @@ __device__ __forceinline__ bool finish_pass_core(float* T12, float* fit_rmse, co
         float Sr[29], E[16];
 #pragma unroll
         for (int i = 0; i < 29; i++) Sr[i] = S[i];
+#ifdef PR_DBG_NOSOLVE      // what-if build (timing only, wrong results): the cost of the solve in the pass-to-pass chain
+        for (int i = 0; i < 16; i++) E[i] = (i % 5 == 0) ? 1.f : 0.f;
+        E[3] = Sr[21] * 1e-9f;
+#else
         if (FAST_SOLVER) solve_666_fast(Sr, E);                // unpack icp.cu:198-205 + solve icp.cu:207
         else solve_666_unrolled(Sr, E);
+#endif
         // result.transformation_ = extrinsic * result.transformation_ (icp.cu:212); geometry.h:107-111
         // sums each dot product from index 3 down to 0.
 #pragma unroll
@@ -230,10 +235,10 @@ icp_pass_kernel(const float* __restrict__ pts, const uint32_t* __restrict__ offs
 // hypothesis-resident driver
 // ---------------------------------------------------------------------------------------------
 #ifndef PR_HYP_WARPS
-#define PR_HYP_WARPS 8
+#define PR_HYP_WARPS 4
 #endif
 #ifndef PR_HYP_MINB
-#define PR_HYP_MINB 2
+#define PR_HYP_MINB 4
 #endif
 #ifndef PR_HYP_ILP
 #define PR_HYP_ILP 4
@@ -247,8 +252,12 @@ icp_pass_kernel(const float* __restrict__ pts, const uint32_t* __restrict__ offs
 #ifndef PR_NN_MINB
 #define PR_NN_MINB 3
 #endif
-constexpr int kTilePts = 256;                  // points per shared-memory tile (3 KB)
+#ifndef PR_TILE_PTS
+#define PR_TILE_PTS 512
+#endif
+constexpr int kTilePts = PR_TILE_PTS;          // points per shared-memory tile (6 KB)
 constexpr int kTileBytes = kTilePts * 12;
+constexpr unsigned kSafePointOffset = 64 + 128;   // bytes from the CTA's state block to its spare point (0, 0, 1): behind T/state and the sums
 constexpr int kMaxStages = 16;                 // tiles per warp ring (wait parities are kept in a 32-bit mask)
 constexpr int kMaxCluster = 8;                 // portable cluster limit
 constexpr int kIlp = PR_HYP_ILP;               // points per lane per group of the projective loop (gathers in flight per lane)
@@ -322,6 +331,12 @@ __device__ __forceinline__ unsigned mapa_u32(unsigned smem_addr, unsigned rank) 
 __device__ __forceinline__ void st_cluster_f32(unsigned addr, float v) {
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+// remote store that signals the destination CTA's mbarrier (complete_tx of 4 bytes): data and notification in one
+// asynchronous operation -- no cluster-wide barrier, no gpu-scope fence (barrier.cluster.arrive.release costs a MEMBAR.GPU)
+__device__ __forceinline__ void st_async_f32(unsigned remote_addr, float v, unsigned remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];"
+                 ::"r"(remote_addr), "f"(v), "r"(remote_bar) : "memory");
+}
 __device__ __forceinline__ void st_cluster_u32(unsigned addr, unsigned v) {
     asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -368,8 +383,10 @@ __device__ __forceinline__ f2_t div2_rn(f2_t a, f2_t b, f2_t r) {       // r = r
     return fma2(e, r, q0);
 }
 __device__ __forceinline__ bool pz_in_exact_range(float pz) {           // false for NaN, too
-    const float a = fabsf(pz);
-    return a >= 8.673617e-19f && a <= 1.1529215e18f;                    // 2^-60 .. 2^60
+    // Only the lower side needs a test: a point with |pz| > 2^60 can never pass the depth gate (|pz - qz| <= max_dist,
+    // qz a depth in metres), whatever pixel it is given, and rcp.approx flushes to zero beyond 2^126, which lands on
+    // pixel (cx, cy) -- inside the image, gate still false.
+    return fabsf(pz) >= 8.673617e-19f;                                  // 2^-60
 }
 // pixel coordinates (as floats, before truncation) of a pair of points.
 // ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even with -fmad=false (it honours .rn only for the
@@ -407,33 +424,58 @@ __device__ __forceinline__ float4 lds128(unsigned addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
-template <int NP, bool TAIL>
-__device__ __forceinline__ void group_projective(const PackedScene& s, unsigned addr, unsigned first, unsigned n,
-                                                 unsigned t_addr, AccP& acc, bool& odd) {
+// The points of one group as a lane holds them: point k of the lane is point (group start + 32 k + lane) of the slice.
+template <int NP> struct GroupPts { float x[2 * NP], y[2 * NP], z[2 * NP]; };
+// Plain coalesced loads, straight from global memory (L2-resident: the cluster re-reads its hypothesis every pass and
+// nothing else touches those lines in between): the three 4-byte loads of a point instruction cover 384 contiguous
+// bytes per warp, and x / y / z of the same lines hit in L1.  The next group is requested as soon as the current one has
+// been transformed, into the same registers, so its latency hides behind projection, gathers and accumulation; no
+// shared-memory tiles, no mbarriers, no per-tile bookkeeping in the loop (the TMA ring this replaces spent 10 % of the
+// kernel's instructions and a quarter of its shared memory there; measured 1.62 -> see DESIGN.md 6.1).
+template <int NP, bool CLAMP>
+__device__ __forceinline__ void load_group(GroupPts<NP>& P, const float* __restrict__ g, unsigned first, unsigned n) {
+#pragma unroll
+    for (int k = 0; k < 2 * NP; k++) {
+        unsigned i = first + 32 * k;
+        if (CLAMP) i = (i < n) ? i : 0u;
+        const float* p = g + 3 * (size_t)i;
+        P.x[k] = __ldg(p); P.y[k] = __ldg(p + 1); P.z[k] = __ldg(p + 2);
+    }
+}
+// One group: transform, project, gather, accumulate.  TAIL: lanes whose points lie past the end of the slice (n) are
+// masked.  PREFETCH: 0 none, 1 the next group unclamped, 2 clamped to the slice.
+template <int NP, bool TAIL, int PREFETCH>
+__device__ __forceinline__ void group_projective(const PackedScene& s, GroupPts<NP>& P, const float* __restrict__ g, unsigned first,
+                                                 unsigned n, unsigned t_addr, AccP& acc, bool& odd) {
     f2_t px[NP], py[NP], pz[NP];
     int idx[2 * NP];
     bool ok[2 * NP];
-    float T[12];
     {
+        float T[12];
         const float4 r0 = lds128(t_addr), r1 = lds128(t_addr + 16), r2 = lds128(t_addr + 32);
         T[0] = r0.x; T[1] = r0.y; T[2] = r0.z; T[3] = r0.w; T[4] = r1.x; T[5] = r1.y; T[6] = r1.z; T[7] = r1.w;
         T[8] = r2.x; T[9] = r2.y; T[10] = r2.z; T[11] = r2.w;
+#pragma unroll
+        for (int j = 0; j < NP; j++) {
+            float x0 = P.x[2 * j], y0 = P.y[2 * j], z0 = P.z[2 * j], x1 = P.x[2 * j + 1], y1 = P.y[2 * j + 1], z1 = P.z[2 * j + 1];
+            if (TAIL) {     // a masked lane holds whatever lies behind the slice: make it the finite point (0, 0, 1)
+                const bool in0 = first + 32 * (2 * j) < n, in1 = first + 32 * (2 * j + 1) < n;
+                x0 = in0 ? x0 : 0.f; y0 = in0 ? y0 : 0.f; z0 = in0 ? z0 : 1.f;
+                x1 = in1 ? x1 : 0.f; y1 = in1 ? y1 : 0.f; z1 = in1 ? z1 : 1.f;
+            }
+            const f2_t x = pk2(x0, x1), y = pk2(y0, y1), z = pk2(z0, z1);
+            // transform_pcd_cuda (icp.cu:147-149) with the accumulated transform, same FMA chain as transform()
+            px[j] = fma2(bc2(T[2]), z, fma2(bc2(T[1]), y, fma2(bc2(T[0]), x, bc2(T[3]))));
+            py[j] = fma2(bc2(T[6]), z, fma2(bc2(T[5]), y, fma2(bc2(T[4]), x, bc2(T[7]))));
+            pz[j] = fma2(bc2(T[10]), z, fma2(bc2(T[9]), y, fma2(bc2(T[8]), x, bc2(T[11]))));
+        }
     }
+    if (PREFETCH == 1) load_group<NP, false>(P, g, first + 64 * NP, n);
+    if (PREFETCH == 2) load_group<NP, true>(P, g, first + 64 * NP, n);
 #pragma unroll
     for (int j = 0; j < NP; j++) {
-        float x0 = lds32(addr + 384 * (2 * j)), y0 = lds32(addr + 384 * (2 * j) + 4), z0 = lds32(addr + 384 * (2 * j) + 8);
-        float x1 = lds32(addr + 384 * (2 * j + 1)), y1 = lds32(addr + 384 * (2 * j + 1) + 4), z1 = lds32(addr + 384 * (2 * j + 1) + 8);
         bool in0 = true, in1 = true;
-        if (TAIL) {     // the tile holds stale data past the end of the slice
-            in0 = first + 32 * (2 * j) < n; in1 = first + 32 * (2 * j + 1) < n;
-            x0 = in0 ? x0 : 0.f; y0 = in0 ? y0 : 0.f; z0 = in0 ? z0 : 1.f;
-            x1 = in1 ? x1 : 0.f; y1 = in1 ? y1 : 0.f; z1 = in1 ? z1 : 1.f;
-        }
-        const f2_t x = pk2(x0, x1), y = pk2(y0, y1), z = pk2(z0, z1);
-        // transform_pcd_cuda (icp.cu:147-149) with the accumulated transform, same FMA chain as transform()
-        px[j] = fma2(bc2(T[2]), z, fma2(bc2(T[1]), y, fma2(bc2(T[0]), x, bc2(T[3]))));
-        py[j] = fma2(bc2(T[6]), z, fma2(bc2(T[5]), y, fma2(bc2(T[4]), x, bc2(T[7]))));
-        pz[j] = fma2(bc2(T[10]), z, fma2(bc2(T[9]), y, fma2(bc2(T[8]), x, bc2(T[11]))));
+        if (TAIL) { in0 = first + 32 * (2 * j) < n; in1 = first + 32 * (2 * j + 1) < n; }
         f2_t uf, vf;
         project_pair(s, px[j], py[j], pz[j], uf, vf);
         float u0, u1, v0, v1, pz0, pz1;
@@ -467,22 +509,33 @@ __device__ __forceinline__ void group_projective(const PackedScene& s, unsigned 
     }
 }
 
-// one tile of a warp's slice (n points in shared memory at `tile`): groups of 32*kIlp points, then 64-point units
-__device__ __forceinline__ void compute_tile(const PackedScene& s, unsigned tile, unsigned n, unsigned t_addr, AccP& acc, bool& odd) {
+// a warp's slice of one hypothesis, one pass: n points at g (global memory)
+#ifndef PR_HYP_UNROLL
+#define PR_HYP_UNROLL 1
+#endif
+constexpr int kHypUnroll = PR_HYP_UNROLL;
+__device__ __forceinline__ void compute_slice(const PackedScene& s, const float* __restrict__ g, unsigned n, bool may_overread,
+                                              unsigned t_addr, AccP& acc, bool& odd) {
     const unsigned lane = threadIdx.x & 31;
-    unsigned addr = tile + 12 * lane;
-    unsigned first = lane;
+    constexpr int NP = kIlp / 2;
     constexpr unsigned kGroup = 32 * kIlp;
-    static_assert(kIlp % 2 == 0 && kTilePts % kGroup == 0, "groups of pairs that tile a tile");
-    const unsigned n_full = n - n % kGroup;
+    static_assert(kIlp % 2 == 0, "groups of pairs");
+    if (n == 0) return;
+    GroupPts<NP> P;
+    unsigned first = lane;
+    if (may_overread) {
+        // the prefetch of the group behind a full group may run up to one group past the slice: other clouds' points or
+        // the buffer's padding, never consumed unmasked
+        const unsigned n_full = n - n % kGroup;
+        load_group<NP, false>(P, g, first, n);
+#pragma unroll kHypUnroll
+        for (; first < n_full; first += kGroup) group_projective<NP, false, 1>(s, P, g, first, n, t_addr, acc, odd);
+        if (n_full < n) group_projective<NP, true, 0>(s, P, g, first, n, t_addr, acc, odd);
+    } else {
+        load_group<NP, true>(P, g, first, n);
 #pragma unroll 1
-    for (; first < n_full; first += kGroup, addr += 12 * kGroup) group_projective<kIlp / 2, false>(s, addr, first, n, t_addr, acc, odd);
-    if (kIlp > 2) {
-        const unsigned n_units = n - n % 64;
-#pragma unroll 1
-        for (; first < n_units; first += 64, addr += 12 * 64) group_projective<1, false>(s, addr, first, n, t_addr, acc, odd);
+        for (; first - lane < n; first += kGroup) group_projective<NP, true, 2>(s, P, g, first, n, t_addr, acc, odd);
     }
-    if (first - lane < n) group_projective<1, true>(s, addr, first, n, t_addr, acc, odd);
 }
 
 // per-point query against the packed scene with the reference's own operations (div.rn.f32): the robust path
@@ -528,25 +581,6 @@ __device__ __forceinline__ void compute_tile(const SceneT& s, unsigned tile, uns
     }
 }
 
-// global -> shared copy of one tile: TMA when the source is 16-byte aligned and the copy, rounded up
-// to 16 bytes, stays inside the point buffer; otherwise the warp copies it with plain loads.
-// Returns true when the TMA path was taken (the consumer then waits on the stage's mbarrier).
-__device__ __forceinline__ bool stage_tile(const float* src, unsigned n, uintptr_t pts_end, unsigned tile, unsigned bar) {
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned bytes = (n * 12 + 15) & ~15u;
-    const bool tma = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (reinterpret_cast<uintptr_t>(src) + bytes <= pts_end);
-    if (tma) {
-        if (lane == 0) {
-            mbar_expect_tx(bar, bytes);
-            tma_load_1d(tile, src, bytes, bar);
-        }
-    } else {
-        for (unsigned i = lane; i < n * 3; i += 32) sts32(tile + 4 * i, src[i]);
-        __syncwarp();
-    }
-    return tma;
-}
-
 // a foreign kd-tree the packed encoding cannot hold (flag raised by nn_pack_nodes_kernel): walk the reference layout
 __device__ __forceinline__ void resolve_scene(PackedScene&) {}
 __device__ __forceinline__ void resolve_scene(PackedNnScene& s) {
@@ -558,11 +592,12 @@ template <class SceneT> struct HypTraits {
     static constexpr int kWarps = kProjective ? PR_HYP_WARPS : PR_NN_WARPS;
     static constexpr int kMinBlocks = kProjective ? PR_HYP_MINB : PR_NN_MINB;
     using Acc = typename std::conditional<kProjective, AccP, AccT>::type;
+    static constexpr size_t kExtraSmem = kProjective ? 0 : (size_t)kTopNodes * 32;     // top levels of the kd-tree
 };
 // dynamic shared memory of a CTA: state | sums | per-warp partials | cluster slots (2 parities) | mbarriers | tile rings
-template <int kWarps> __host__ __device__ constexpr size_t hyp_fixed_smem() { return 64 + 128 + (size_t)kWarps * 128 + 2 * kMaxCluster * 128; }
-template <int kWarps> constexpr size_t hyp_smem(int n_stages) {
-    return hyp_fixed_smem<kWarps>() + (size_t)kWarps * (kMaxStages * 8) + (size_t)kWarps * n_stages * kTileBytes;
+template <int kWarps> __host__ __device__ constexpr size_t hyp_fixed_smem() { return 64 + 128 + 64 + 64 + (size_t)kWarps * 128 + 2 * kMaxCluster * 128; }
+template <int kWarps> constexpr size_t hyp_smem(int n_stages, size_t extra) {
+    return hyp_fixed_smem<kWarps>() + (size_t)kWarps * (kMaxStages * 8) + extra + (size_t)kWarps * n_stages * kTileBytes;
 }
 
 // state words behind the 12 floats of T
@@ -605,24 +640,47 @@ icp_hyp_kernel(const float* __restrict__ pts, size_t capacity_points, const uint
     // dynamic shared memory: state | sums | per-warp partials | cluster slots | mbarriers | tile rings
     float* s_T = reinterpret_cast<float*>(smem_raw);     // [12] T, then fitness, rmse, done, hypothesis id
     float* s_S = s_T + 16;                               // [32]: the hypothesis' sums of this pass
-    float* s_part = s_S + 32;                            // [kWarps][32]
+    float* s_safe = s_S + 32;                            // [3] the spare point (0, 0, 1) masked lanes read (+ padding to 64 bytes)
+    float* s_xbar = s_safe + 16;                         // two mbarriers (one per pass parity): the peers' partials have arrived
+    float* s_part = s_xbar + 16;                         // [kWarps][32]
     float* s_cl = s_part + kWarps * 32;                  // [2][kMaxCluster][32]: CTA partials of the cluster, by pass parity
     volatile unsigned* s_w = reinterpret_cast<volatile unsigned*>(s_T);
     const unsigned smem0 = smem_u32(smem_raw);
     const unsigned bar0 = smem0 + (unsigned)hyp_fixed_smem<kWarps>() + warp * (kMaxStages * 8);
-    const unsigned tile0 = smem0 + (unsigned)hyp_fixed_smem<kWarps>() + kWarps * (kMaxStages * 8) + warp * (unsigned)n_stages * kTileBytes;
+    const unsigned extra0 = smem0 + (unsigned)hyp_fixed_smem<kWarps>() + kWarps * (kMaxStages * 8);
+    const unsigned tile0 = extra0 + (unsigned)Tr::kExtraSmem + warp * (unsigned)n_stages * kTileBytes;
     const uintptr_t pts_end = reinterpret_cast<uintptr_t>(pts) + capacity_points * 12;
 
     SceneT sc = scene;
     resolve_scene(sc);
+    if (threadIdx.x < 3) s_safe[threadIdx.x] = (threadIdx.x == 2) ? 1.f : 0.f;
     if (lane == 0) {
         for (int s = 0; s < n_stages; s++) mbar_init(bar0 + 8 * s, 1);
+        if (warp == 0) { mbar_init(smem_u32(s_xbar), 1); mbar_init(smem_u32(s_xbar) + 8, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    unsigned xph = 0;                   // warp 0: bit p = parity to wait for on the exchange barrier of pass parity p
     __syncwarp();
+    unsigned par = 0;                   // bit s = parity to wait for on stage s of this warp's ring
+    if constexpr (!Tr::kProjective) {
+        // kd-tree: nodes [0, n_top) = the top levels (breadth-first numbering) -> shared memory, one TMA bulk copy
+        const int n_top = sc.nodes ? min(sc.n_nodes, kTopNodes) : 0;
+        if (n_top > 0) {
+            if (warp == 0) {
+                if (lane == 0) {
+                    mbar_expect_tx(bar0, (unsigned)n_top * 32);
+                    tma_load_1d(extra0, sc.nodes, (unsigned)n_top * 32, bar0);
+                }
+                mbar_wait(bar0, 0);
+                par ^= 1u;
+            }
+            sc.top = reinterpret_cast<const float4*>(smem_raw + (extra0 - smem0));
+            sc.n_top = n_top;
+        }
+        __syncthreads();
+    }
     if (C > 1) cluster_sync_all();      // every CTA of the cluster is running before its shared memory is written remotely
 
-    unsigned par = 0;                   // bit s = parity to wait for on stage s of this warp's ring
     for (;;) {
         // ---- claim a hypothesis for the cluster
         if (C > 1) {
@@ -650,41 +708,63 @@ icp_hyp_kernel(const float* __restrict__ pts, size_t capacity_points, const uint
         const unsigned first_pt = (g * ubase + min(g, urem)) << 6;
         const unsigned n_mine = my_units ? min(my_units << 6, n - first_pt) : 0u;
         const float* gsl = pts + 3 * ((size_t)offsets[h] + first_pt);
-        const unsigned nt = (n_mine + kTilePts - 1) / kTilePts;
+        // ---- where the slice comes from.  Projective: straight from global memory, one group ahead, in registers
+        // (compute_slice).  Nearest neighbour: through the warp's ring of shared-memory tiles, filled by TMA.
+        [[maybe_unused]] bool may_overread = false;
+        if constexpr (Tr::kProjective) {
+            constexpr unsigned kGroup = 32 * kIlp;
+            may_overread = reinterpret_cast<uintptr_t>(gsl) + 12ull * (n_mine - n_mine % kGroup + 2 * kGroup) <= pts_end;
+        }
+        const unsigned nt = Tr::kProjective ? 0u : (n_mine + kTilePts - 1) / kTilePts;
         const bool resident = nt <= (unsigned)n_stages;          // the slice stays in shared memory for all passes
-        const unsigned total_visits = resident ? nt : nt * (unsigned)(crit.max_iteration + 1);
-        unsigned issued = 0, consumed = 0;      // tile visits whose load has been issued / waited for
+        // TMA needs a 16-byte aligned source (offsets padded to 4 points give that) and a copy that, rounded up to 16
+        // bytes, stays inside the point buffer; otherwise the warp copies its tiles with plain loads
+        const bool use_tma = ((reinterpret_cast<uintptr_t>(gsl) & 15) == 0) &&
+                             (reinterpret_cast<uintptr_t>(gsl) + ((n_mine * 12 + 15) & ~15u) <= pts_end);
+        unsigned to_issue = resident ? nt : nt * (unsigned)(crit.max_iteration + 1);     // tile loads still to issue
+        unsigned in_flight = 0;                 // tile loads issued and not yet waited for
         unsigned itile = 0, istage = 0;         // tile and stage of the next load
-        unsigned cstage = 0;                    // stage of the next visit to consume (streaming)
-        unsigned tma_mask = 0;                  // bit s: the load into stage s went through TMA
+        unsigned cstage = 0;                    // stage of the next tile to consume (streaming)
         auto issue_one = [&]() {
             const unsigned np = min((unsigned)kTilePts, n_mine - itile * kTilePts);
-            const bool tma = stage_tile(gsl + (size_t)itile * (kTilePts * 3), np, pts_end, tile0 + istage * kTileBytes, bar0 + 8 * istage);
-            tma_mask = tma ? (tma_mask | (1u << istage)) : (tma_mask & ~(1u << istage));
-            issued++;
+            const float* src = gsl + (size_t)itile * (kTilePts * 3);
+            const unsigned dst = tile0 + istage * kTileBytes;
+            if (use_tma) {
+                if (lane == 0) {
+                    const unsigned bytes = (np * 12 + 15) & ~15u;
+                    mbar_expect_tx(bar0 + 8 * istage, bytes);
+                    tma_load_1d(dst, src, bytes, bar0 + 8 * istage);
+                }
+            } else {
+                for (unsigned i = lane; i < np * 3; i += 32) sts32(dst + 4 * i, src[i]);
+                __syncwarp();
+            }
             itile = (itile + 1 == nt) ? 0 : itile + 1;
             istage = (istage + 1 == (unsigned)n_stages) ? 0 : istage + 1;
+            to_issue--; in_flight++;
         };
-        while (issued < min((unsigned)n_stages, total_visits)) issue_one();
+        for (unsigned k = min((unsigned)n_stages, to_issue); k; k--) issue_one();
 
         for (int pass = 0;; pass++) {
             const unsigned t_addr = smem_u32(s_T);
             typename Tr::Acc acc;
             acc_zero(acc);
             bool odd = false;
+            if constexpr (Tr::kProjective) compute_slice(sc, gsl, n_mine, may_overread, t_addr, acc, odd);
             for (unsigned t = 0; t < nt; t++) {
                 const unsigned stage = resident ? t : cstage;
                 if (!resident || pass == 0) {
-                    if (tma_mask & (1u << stage)) {
+                    if (use_tma) {
                         mbar_wait(bar0 + 8 * stage, (par >> stage) & 1u);
                         par ^= (1u << stage);
                     }
-                    consumed++;
+                    in_flight--;
                 }
-                compute_tile(sc, tile0 + stage * kTileBytes, min((unsigned)kTilePts, n_mine - t * kTilePts), t_addr, acc, odd);
+                if constexpr (!Tr::kProjective)
+                    compute_tile(sc, tile0 + stage * kTileBytes, min((unsigned)kTilePts, n_mine - t * kTilePts), t_addr, acc, odd);
                 if (!resident) {
                     __syncwarp();            // every lane is done reading this stage before it is refilled
-                    if (issued < total_visits) issue_one();
+                    if (to_issue) issue_one();
                     cstage = (cstage + 1 == (unsigned)n_stages) ? 0 : cstage + 1;
                 }
             }
@@ -697,22 +777,28 @@ icp_hyp_kernel(const float* __restrict__ pts, size_t capacity_points, const uint
             }
             s_part[warp * 32 + lane] = mine;
             __syncthreads();
-            const unsigned slot = (unsigned)(pass & 1) * (kMaxCluster * 32);
+            const unsigned pp = (unsigned)(pass & 1);
+            const unsigned slot = pp * (kMaxCluster * 32);
             if (warp == 0) {
                 float s = 0.f;
 #pragma unroll
                 for (int w = 0; w < kWarps; w++) s += s_part[w * 32 + lane];         // fixed order
+                s_cl[slot + rank * 32 + lane] = s;
                 if (C > 1) {
+                    // every CTA sends its partial to every peer (st.async: the store completes 4 bytes on the peer's
+                    // mbarrier of this pass parity) and waits until its own barrier has seen the peers' 128 bytes each.
+                    // A peer can be at most one pass ahead (it needs this CTA's partial to finish its pass), so two
+                    // slots / two barriers by pass parity never collide.
+                    const unsigned xb = smem_u32(s_xbar) + 8 * pp;
+                    if (lane == 0) mbar_expect_tx(xb, (C - 1) * 128);
                     const unsigned mine_addr = smem_u32(s_cl + slot + rank * 32 + lane);
-                    for (unsigned r = 0; r < C; r++) st_cluster_f32(mapa_u32(mine_addr, r), s);
-                } else {
-                    s_cl[slot + lane] = s;
+                    for (unsigned r = 0; r < C; r++)
+                        if (r != rank) st_async_f32(mapa_u32(mine_addr, r), s, mapa_u32(xb, r));
+                    mbar_wait(xb, (xph >> pp) & 1u);
+                    xph ^= (1u << pp);
                 }
-            }
-            if (C > 1) cluster_sync_all();      // release/acquire: every CTA's partial is in every CTA's slots
-            if (warp == 0) {
-                if (C == 1) __syncwarp();
-                float s = 0.f;
+                __syncwarp();
+                s = 0.f;
                 for (unsigned r = 0; r < C; r++) s += s_cl[slot + r * 32 + lane];      // rank order: same bits in every CTA
                 s_S[lane] = s;
                 if (out32 && pass == 0 && rank == 0) out32[(size_t)h * 32 + lane] = s;
@@ -725,13 +811,12 @@ icp_hyp_kernel(const float* __restrict__ pts, size_t capacity_points, const uint
             if (s_w[kStDone]) break;
         }
         // ---- loads issued ahead of a pass that never ran: wait for them before the ring is reused
-        while (consumed < issued) {
-            const unsigned stage = resident ? consumed : cstage;
-            if (tma_mask & (1u << stage)) {
-                mbar_wait(bar0 + 8 * stage, (par >> stage) & 1u);
-                par ^= (1u << stage);
+        while (in_flight) {
+            if (use_tma) {
+                mbar_wait(bar0 + 8 * cstage, (par >> cstage) & 1u);
+                par ^= (1u << cstage);
             }
-            consumed++;
+            in_flight--;
             cstage = (cstage + 1 == (unsigned)n_stages) ? 0 : cstage + 1;
         }
         __syncwarp();
@@ -903,9 +988,9 @@ int launch_hyp(const float* pts_dev, size_t capacity_points, const uint32_t* off
     // tile ring: as many stages as fit next to kMinBlocks - 1 other CTAs (1 KB per CTA is reserved by the system)
     const size_t sm_total = 233472;      // 228 KB of shared memory per SM
     size_t budget = std::min(di.smem_optin, sm_total / (size_t)Tr::kMinBlocks - 1024);
-    int n_stages = (int)((budget - hyp_smem<Tr::kWarps>(0)) / ((size_t)Tr::kWarps * kTileBytes));
-    n_stages = std::max(2, std::min(kMaxStages, n_stages));
-    const size_t smem = hyp_smem<Tr::kWarps>(n_stages);
+    int n_stages = (int)((budget - hyp_smem<Tr::kWarps>(0, Tr::kExtraSmem)) / ((size_t)Tr::kWarps * kTileBytes));
+    n_stages = Tr::kProjective ? 0 : std::max(2, std::min(kMaxStages, n_stages));
+    const size_t smem = hyp_smem<Tr::kWarps>(n_stages, Tr::kExtraSmem);
     auto kernel = icp_hyp_kernel<SceneT>;
     PR_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int C = pick_cluster(n_hyp, di.sms, Tr::kMinBlocks);
@@ -1138,7 +1223,7 @@ int pr_icp_nn_batch(float* pts_dev, const uint32_t* offsets_dev, const uint32_t*
     if (workspace_bytes < ws.bytes) return PR_ERR_WORKSPACE_TOO_SMALL;
     PackedNnScene ps;
     ps.max_dist_sq = s.max_dist_sq; ps.nrm = s.nrm; ps.n_nodes = s.n_nodes; ps.ref = s;
-    ps.nodes = nullptr; ps.pts4 = nullptr; ps.unsupported = nullptr;
+    ps.nodes = nullptr; ps.pts4 = nullptr; ps.unsupported = nullptr; ps.top = nullptr; ps.n_top = 0;
     if (!(flags & PR_ICP_REFERENCE_ARITHMETIC) && s.n_nodes > 0) {
         const PackedTree t = carve_packed_tree(ws.packed, scene->n_points, scene->n_nodes);
         rc = pack_tree(s, scene->n_points, t, stream);
@@ -1207,7 +1292,7 @@ int pr_pass_sums_nn(const float* pts_dev, const uint32_t* offsets_dev, const uin
     cudaStream_t stream = as_stream(stream_);
     PackedNnScene ps;
     ps.max_dist_sq = s.max_dist_sq; ps.nrm = s.nrm; ps.n_nodes = s.n_nodes; ps.ref = s;
-    ps.nodes = nullptr; ps.pts4 = nullptr; ps.unsupported = nullptr;
+    ps.nodes = nullptr; ps.pts4 = nullptr; ps.unsupported = nullptr; ps.top = nullptr; ps.n_top = 0;
     if (s.n_nodes > 0) {
         const PackedTree t = carve_packed_tree(ws.packed, scene->n_points, scene->n_nodes);
         rc = pack_tree(s, scene->n_points, t, stream);
@@ -1256,7 +1341,7 @@ int pr_correspondences_nn(const float* pts_dev, size_t n, const pr_scene_nn* sce
     if (rc != PR_OK) return rc;
     PackedNnScene ps;
     ps.max_dist_sq = s.max_dist_sq; ps.nrm = s.nrm; ps.n_nodes = s.n_nodes; ps.ref = s;
-    ps.nodes = t.nodes; ps.pts4 = t.pts4; ps.unsupported = t.flag;
+    ps.nodes = t.nodes; ps.pts4 = t.pts4; ps.unsupported = t.flag; ps.top = nullptr; ps.n_top = 0;
     corr_nn_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pts_dev, (unsigned)n, ps, idx_dev);
     count_launch();
     PR_LAUNCH_CHECK();

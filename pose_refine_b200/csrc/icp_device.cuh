@@ -118,16 +118,26 @@ __device__ __forceinline__ bool query(const NnScene& s, float px, float py, floa
 // ---------------------------------------------------------------------------------------------
 // Packed kd-tree for the hypothesis-resident driver.  Same tree (same nodes, same leaf ranges, same points) as
 // the reference's Node_kdtree array, re-laid out per ICP call so that a node is two aligned float4:
-//     {lo.x, lo.y, lo.z, a}   {hi.x, hi.y, hi.z, unused}
-// a >= 0: internal node, children a and a+1 (build_tree appends them together, pcd_scene.cpp:160-170);
-// a <  0: leaf, a = 0x80000000 | count << 24 | left.  [lo,hi] is the box of the node's OWN points --
-// computed here for leaves too (the reference stores none for leaves, pcd_scene.h:14-19).
-// The query is an exact nearest-neighbour search like Scene_nn::query, but it prunes with the box of
-// the CHILD it is about to enter (the reference prunes with the box of the node it re-visits, which is
-// much weaker: 385 node visits per query on the fixture vs ~20-40 here), starts
-// from best = max_dist^2 (anything farther is invalid anyway, pcd_scene.h:127) and keeps the far
-// children on a small explicit stack.  Distances use the reference's operation order, so the winner is
-// the same point except for exact distance ties between points of different leaves.
+//     {lo.x, lo.y, lo.z, a}   {hi.x, hi.y, hi.z, split_v}
+// a >= 0: internal node, a = split_dim << 28 | child1, children child1 and child1 + 1 (build_tree appends them together,
+// pcd_scene.cpp:160-170); a < 0: leaf, a = 0x80000000 | count << 24 | left.  [lo,hi] is the box of the node's OWN
+// points -- computed here for leaves too (the reference stores none for leaves, pcd_scene.h:14-19).
+// build_tree numbers the nodes generation by generation (breadth first), so nodes [0, kTopNodes) ARE the top levels
+// of the tree: the kernel keeps them in shared memory (one TMA bulk copy per CTA), deeper nodes come through L1/L2.
+//
+// The query is an exact nearest-neighbour search that returns the SAME point as Scene_nn::query, ties included:
+//   * same visiting order: at an internal node the child on the query's side of the split plane first
+//     (pcd_scene.h:92-100), the other one afterwards; leaves scan [left, right) in order;
+//   * same update rule: strict <, so among points at exactly the minimum distance the first one visited wins
+//     (pcd_scene.h:88-90);
+//   * pruning never removes that winner: a subtree is skipped only when the distance to the box of its own points,
+//     scaled by 0.99999 (the bound is a rounded float), is >= the best distance so far -- a point that is at least as
+//     near as the current best is strictly inside that margin.  The reference prunes with the box of the node it
+//     RE-VISITS (much weaker: 385 node visits per query on the fixture vs ~20-40 here); both
+//     walks visit the winner's leaf, in the same relative order.
+// It starts from best = max_dist^2 (anything farther is invalid anyway, pcd_scene.h:127) and parks the far children
+// (ids only; the bound is recomputed from the box when the node is fetched) on a small explicit stack.
+constexpr int kTopNodes = 512;            // 16 KB of shared memory: the top 9 levels
 struct PackedNnScene {
     float max_dist_sq;
     const float4* nodes;      // 2 per node
@@ -135,6 +145,8 @@ struct PackedNnScene {
     const float* nrm;         // original Vec3f normals
     int n_nodes;
     const unsigned* unsupported;   // device flag raised by nn_pack_nodes_kernel: this tree does not fit the encoding
+    const float4* top;        // shared-memory copy of nodes [0, n_top) (set by the kernel; nullptr: none)
+    int n_top;
     NnScene ref;              // the reference layout (fallback walk when the stack would overflow)
 };
 
@@ -143,7 +155,8 @@ nn_pack_points_kernel(const float* __restrict__ pcd, size_t n, float4* __restric
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i < n) pts4[i] = make_float4(pcd[3 * i], pcd[3 * i + 1], pcd[3 * i + 2], 0.f);
 }
-// sets *unsupported when a leaf does not fit the packed encoding (more than 127 points or left >= 2^24)
+// sets *unsupported when the tree does not fit the packed encoding (a leaf of more than 127 points, left >= 2^24,
+// children that are not siblings, a child index >= 2^28)
 __global__ void __launch_bounds__(256)
 nn_pack_nodes_kernel(const pr_node_kdtree* __restrict__ nodes, int n_nodes, const float* __restrict__ pcd,
                      float4* __restrict__ out, unsigned* __restrict__ unsupported) {
@@ -152,6 +165,7 @@ nn_pack_nodes_kernel(const pr_node_kdtree* __restrict__ nodes, int n_nodes, cons
     const pr_node_kdtree nd = nodes[i];
     float lo[3], hi[3];
     int a;
+    float w = 0.f;
     if (nd.child1 < 0 || nd.child2 < 0) {
         const int cnt = nd.right - nd.left;
         if (cnt < 0 || cnt > 127 || nd.left < 0 || nd.left >= (1 << 24)) { *unsupported = 1; return; }
@@ -160,12 +174,13 @@ nn_pack_nodes_kernel(const pr_node_kdtree* __restrict__ nodes, int n_nodes, cons
             for (int k = 0; k < 3; k++) { const float v = pcd[3 * j + k]; lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v); }
         a = (int)(0x80000000u | ((unsigned)cnt << 24) | (unsigned)nd.left);
     } else {
-        if (nd.child2 != nd.child1 + 1) { *unsupported = 1; return; }
+        if (nd.child2 != nd.child1 + 1 || nd.child1 >= (1 << 28) || nd.split_dim < 0 || nd.split_dim > 2) { *unsupported = 1; return; }
         for (int k = 0; k < 3; k++) { lo[k] = nd.bbox[2 * k]; hi[k] = nd.bbox[2 * k + 1]; }
-        a = nd.child1;
+        a = nd.child1 | (nd.split_dim << 28);
+        w = nd.split_v;
     }
     out[2 * i] = make_float4(lo[0], lo[1], lo[2], __int_as_float(a));
-    out[2 * i + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    out[2 * i + 1] = make_float4(hi[0], hi[1], hi[2], w);
 }
 
 __device__ __forceinline__ float box_dist_sq(const float4& lo, const float4& hi, float px, float py, float pz) {
@@ -174,6 +189,11 @@ __device__ __forceinline__ float box_dist_sq(const float4& lo, const float4& hi,
     const float dz = fmaxf(fmaxf(lo.z - pz, pz - hi.z), 0.f);
     return dx * dx + dy * dy + dz * dz;
 }
+// node i of the packed tree: top levels from shared memory, the rest through the read-only path
+__device__ __forceinline__ void load_node(const PackedNnScene& s, int i, float4& lo, float4& hi) {
+    if (i < s.n_top) { lo = s.top[2 * i]; hi = s.top[2 * i + 1]; }
+    else { lo = __ldg(s.nodes + 2 * i); hi = __ldg(s.nodes + 2 * i + 1); }
+}
 
 // exact nearest neighbour over the packed tree: index of the winner (leaf order), or -1 when nothing is nearer
 // than max_dist.  -2: the explicit stack overflowed (the caller falls back to the reference walk).
@@ -181,13 +201,12 @@ __device__ __forceinline__ int nn_search_packed(const PackedNnScene& s, float px
     if (s.n_nodes <= 0) return -1;
     constexpr int kStack = 24;       // far children parked: one per level at most (trees here are <= 20 deep)
     int stack_n[kStack];
-    float stack_lb[kStack];
     int sp = 0;
     float best = s.max_dist_sq;
     int best_i = -1;
     bool overflow = false;
-    float4 lo = __ldg(s.nodes), hi = __ldg(s.nodes + 1);
-    // a box lower bound is rounded, so it is trusted only with a 1e-5 margin
+    float4 lo, hi;
+    load_node(s, 0, lo, hi);
     bool go = box_dist_sq(lo, hi, px, py, pz) * 0.99999f < best;
     while (go) {
         const int a = __float_as_int(lo.w);
@@ -201,26 +220,18 @@ __device__ __forceinline__ int nn_search_packed(const PackedNnScene& s, float px
             }
             go = false;
         } else {
-            const float4 lo1 = __ldg(s.nodes + 2 * a), hi1 = __ldg(s.nodes + 2 * a + 1);
-            const float4 lo2 = __ldg(s.nodes + 2 * a + 2), hi2 = __ldg(s.nodes + 2 * a + 3);
-            const float lb1 = box_dist_sq(lo1, hi1, px, py, pz) * 0.99999f, lb2 = box_dist_sq(lo2, hi2, px, py, pz) * 0.99999f;
-            const bool first1 = lb1 <= lb2;
-            const float lb_near = first1 ? lb1 : lb2, lb_far = first1 ? lb2 : lb1;
-            if (lb_far < best) {
-                if (sp < kStack) { stack_n[sp] = first1 ? a + 1 : a; stack_lb[sp] = lb_far; sp++; }
-                else overflow = true;
-            }
-            if (lb_near < best) { lo = first1 ? lo1 : lo2; hi = first1 ? hi1 : hi2; continue; }
+            const int dim = a >> 28, c1 = a & 0xFFFFFFF;
+            const float diff = (dim == 0 ? px : (dim == 1 ? py : pz)) - hi.w;            // pcd_scene.h:92-95
+            const int near_c = (diff < 0.f) ? c1 : c1 + 1, far_c = (diff < 0.f) ? c1 + 1 : c1;
+            if (sp < kStack) stack_n[sp++] = far_c; else overflow = true;
+            load_node(s, near_c, lo, hi);
+            if (box_dist_sq(lo, hi, px, py, pz) * 0.99999f < best) continue;
             go = false;
         }
         while (sp > 0) {
-            --sp;
-            if (stack_lb[sp] < best) {
-                const int n = stack_n[sp];
-                lo = __ldg(s.nodes + 2 * n); hi = __ldg(s.nodes + 2 * n + 1);
-                go = true;
-                break;
-            }
+            const int n = stack_n[--sp];
+            load_node(s, n, lo, hi);
+            if (box_dist_sq(lo, hi, px, py, pz) * 0.99999f < best) { go = true; break; }
         }
     }
     return overflow ? -2 : best_i;

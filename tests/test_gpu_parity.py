@@ -363,8 +363,9 @@ def test_pass_sums_of_the_shipped_kernel(api, port, mesh, fixture_scene, golden,
             q, n, valid = port.query(pscene, cloud)
             terms = _terms_f64(cloud, q, n, valid)
             truth, mag = terms.sum(0), np.abs(terms).sum(0)
-            assert got[i, 28] == truth[28], f"cloud {i}: inlier count {got[i, 28]} vs {truth[28]}"
-            assert np.all(np.abs(got[i] - truth) <= 2e-6 * mag + 1e-30), (i, (got[i] - truth) / np.maximum(mag, 1e-30))
+            kind = type(scene).__name__
+            assert got[i, 28] == truth[28], f"{kind} cloud {i}: inlier count {got[i, 28]} vs {truth[28]}"
+            assert np.all(np.abs(got[i] - truth) <= 2e-6 * mag + 1e-30), (kind, i, (got[i] - truth) / np.maximum(mag, 1e-30))
 
 
 def _moved(cloud, seed):
@@ -408,6 +409,39 @@ def test_correspondences_projective_match_the_oracle_point_by_point(api, port, m
     print(f"projective correspondences: {mismatches} mismatches in {total} points ({inliers} inliers)")
     assert inliers > 0.5 * total
     assert mismatches == 0
+
+
+def test_correspondences_nn_match_the_oracle_point_by_point(api, port, mesh, fixture_scene, golden):
+    """The packed kd-tree search of the hot loop against Scene_nn::query (pcd_scene.h:61-136), index by index: the
+    fixture scene, a 100k-point composited scene (C3) and a fronto-parallel patch full of exact distance ties.
+    Pinned: 0 mismatches (the packed walk keeps the reference's visiting order and strict-< rule, so ties agree too)."""
+    arrays, _ = golden
+    K = arrays["K"]
+    pts, offsets, counts = _hyp8_clouds(api, mesh, arrays)
+    h_pts, h_off, h_cnt = pts.cpu().numpy(), offsets.cpu().numpy(), counts.cpu().numpy()
+    clouds = [fixture_scene["cloud"]] + [h_pts[h_off[i]: h_off[i] + h_cnt[i]] for i in range(3)]
+    flat = np.zeros((480, 640), np.int32)
+    flat[100:380, 120:520] = 300                       # every pixel at the same depth: a lattice of equidistant points
+    lattice = port.depth2cloud(flat, K)[::7].copy()
+    lattice[:, 2] += np.float32(0.004)                 # queries in front of the lattice, many exactly between points
+    scenes = [("fixture", fixture_scene["scene_depth"], clouds),
+              ("c3-100k", wl.plane_scene_depth(fixture_scene["scene_depth"], 100000), clouds[:2]),
+              ("tie-rich", flat, [lattice, _moved(lattice, 5)])]
+    total = mismatches = 0
+    for name, depth, qs in scenes:
+        sn = api.SceneNN().init_cuda(depth, K)
+        pn = port.scene_nn(depth, K)
+        for ci, cloud in enumerate(qs):
+            for variant in range(2):
+                c = cloud if variant == 0 else _moved(cloud, 10 * ci + variant)
+                got = api.correspondences(c, sn)
+                want, _, _ = port.query_nn_stats(pn, c)
+                q, n, valid = port.query(pn, c)
+                want = np.where(valid, want, -1)
+                bad = int((got != want).sum())
+                total += len(c); mismatches += bad
+                assert bad == 0, f"{name} cloud {ci} variant {variant}: {bad} of {len(c)} nearest neighbours differ"
+    print(f"nn correspondences: {mismatches} mismatches in {total} queries")
 
 
 def test_fast_solver_matches_exact(api, port, fixture_scene, golden):
@@ -623,6 +657,10 @@ def test_full_size_properties(api, port, mesh, fixture_scene, golden, torch_mod)
     bad = reproducible & (err_best > np.maximum(REL_TOL * scale, 3 * spread))
     assert not bad.any(), f"hypotheses {np.nonzero(bad)[0][:10]}: err {err_best[bad][:10]}, oracle spread {spread[bad][:10]}"
     # the statistics of the reproducible ones follow
-    ok = reproducible & ~beyond
-    assert np.all(np.abs(r[ok, 17] - want[0, ok, 17]) <= STAT_TOL * np.maximum(want[0, ok, 17], 1e-12))
-    assert np.all(np.abs(r[ok, 16] - want[0, ok, 16]) <= STAT_TOL * np.maximum(want[0, ok, 16], 1e-12))
+    # a pose change of e moves a point 0.3 m from the origin by 0.3 e, i.e. rmse (2 - 4 mm) by up to ~100 e relative:
+    # the bar on the statistics is STAT_TOL or 300 x the hypothesis' own pose deviation, whichever is larger
+    ok = reproducible & ~beyond & converging
+    tol = np.maximum(STAT_TOL, 300 * err[ok])
+    dfit, drmse = np.abs(r[ok, 17] - want[0, ok, 17]), np.abs(r[ok, 16] - want[0, ok, 16])
+    assert np.all(dfit <= tol * want[0, ok, 17]), (np.nonzero(ok)[0][dfit > tol * want[0, ok, 17]], dfit.max())
+    assert np.all(drmse <= tol * want[0, ok, 16]), (np.nonzero(ok)[0][drmse > tol * want[0, ok, 16]], drmse.max())
