@@ -657,10 +657,12 @@ def test_full_size_properties(api, port, mesh, fixture_scene, golden, torch_mod)
     bad = reproducible & (err_best > np.maximum(REL_TOL * scale, 3 * spread))
     assert not bad.any(), f"hypotheses {np.nonzero(bad)[0][:10]}: err {err_best[bad][:10]}, oracle spread {spread[bad][:10]}"
     # the statistics of the reproducible ones follow
-    # a pose change of e moves a point 0.3 m from the origin by 0.3 e, i.e. rmse (2 - 4 mm) by up to ~100 e relative:
-    # the bar on the statistics is STAT_TOL or 300 x the hypothesis' own pose deviation, whichever is larger
+    # fitness counts inliers (one flipped inlier of ~22,000 = 5e-5).  rmse is far more sensitive to the SAME flips: the
+    # gate is at 0.1 m while a converged residual is ~3 mm, so ONE point that crosses the gate (d^2 = 1e-2 against a
+    # total of ~22,000 x 1e-5 = 0.2) moves rmse by 2.5 % -- the bar on rmse over the whole batch is two such flips
     ok = reproducible & ~beyond & converging
-    tol = np.maximum(STAT_TOL, 300 * err[ok])
     dfit, drmse = np.abs(r[ok, 17] - want[0, ok, 17]), np.abs(r[ok, 16] - want[0, ok, 16])
-    assert np.all(dfit <= tol * want[0, ok, 17]), (np.nonzero(ok)[0][dfit > tol * want[0, ok, 17]], dfit.max())
-    assert np.all(drmse <= tol * want[0, ok, 16]), (np.nonzero(ok)[0][drmse > tol * want[0, ok, 16]], drmse.max())
+    assert np.all(dfit <= STAT_TOL * want[0, ok, 17]), (np.nonzero(ok)[0][dfit > STAT_TOL * want[0, ok, 17]], dfit.max())
+    assert np.all(drmse <= 5e-2 * want[0, ok, 16]), (np.nonzero(ok)[0][drmse > 5e-2 * want[0, ok, 16]], drmse.max())
+    print(f"statistics of the {int(ok.sum())} reproducible converging hypotheses: max relative fitness diff "
+          f"{(dfit / want[0, ok, 17]).max():.2e}, rmse diff {(drmse / want[0, ok, 16]).max():.2e}")
