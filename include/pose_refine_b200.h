@@ -161,6 +161,11 @@ int pr_render_cloud_batch(const float* verts_dev, size_t n_verts, const int32_t*
                           const pr_mesh_clusters* clusters /* nullable; faces must then be pr_mesh_cluster's order */,
                           void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
 
+/* Parity entry point: the rasteriser divides with a refined reciprocal + residual correction instead of the       */
+/* div.rn.f32 call (raster.cu, "IEEE division without the library call").  Compares n pseudo-random quotients      */
+/* over the operand ranges the kernel guarantees with div.rn.f32; *mismatches_dev (uint64) must end up 0.          */
+int pr_debug_div_check(uint64_t n, uint32_t seed, uint64_t* mismatches_dev, pr_stream_t stream);
+
 /* raw2depth_uint16_cuda / raw2mask_uint8_cuda / raw2depth_mask_cuda (renderer.cu:338-439):      */
 /* depth = uint16_t(raw), mask = raw > 0 ? 255 : 0.  Either output may be NULL.                  */
 int pr_raw2depth_mask(const int32_t* raw_dev, size_t n, uint16_t* depth_dev, uint8_t* mask_dev, pr_stream_t stream);

@@ -73,6 +73,7 @@ PROTOTYPES = {
     "pr_refiner_run_device": (_i, [_vp, _vp, _sz, Criteria, _vp, _vp]),
     "pr_refiner_buffers": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "pr_launch_count": (C.c_uint64, []),
+    "pr_debug_div_check": (_i, [C.c_uint64, _u32, _vp, _vp]),
     "pr_scene_projective_packed_bytes": (_sz, [_u32, _u32]),
     "pr_scene_projective_pack": (_i, [C.POINTER(SceneProjective), _vp, _vp]),
     "pr_icp_projective_batch_packed": (_i, [_vp, _vp, _vp, _sz, _sz, C.POINTER(SceneProjective), _vp, Criteria, _vp, _i, _vp, _sz, _vp]),

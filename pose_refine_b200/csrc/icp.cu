@@ -961,18 +961,21 @@ inline int device_info(DeviceInfo& out) {
 // C is the reduce -> cluster barrier -> solve chain (~1.5 us), so C is kept as small as the batch allows: enough
 // hypotheses per cluster slot that the claim counter balances the SMs, larger clusters only for small batches,
 // where otherwise most SMs would have nothing to do.
-#ifndef PR_HYP_CLUSTER_BIG
-#define PR_HYP_CLUSTER_BIG 4
+#ifndef PR_HYP_CLUSTER_MIN
+#define PR_HYP_CLUSTER_MIN 2
 #endif
 inline int pick_cluster(size_t n_hyp, int sms, int min_blocks) {
 #ifdef PR_DEBUG       // experiment builds only (scripts/build_variants.py)
     if (const char* e = getenv("PR_HYP_CLUSTER")) { const int c = atoi(e); if (c == 1 || c == 2 || c == 4 || c == 8) return c; }
 #endif
     if (PR_HYP_CLUSTER > 0) return PR_HYP_CLUSTER;
-    const size_t slots = (size_t)sms * (size_t)min_blocks;    // CTAs that can be resident
-    int c = 1;
-    while (c < kMaxCluster && n_hyp * (size_t)(2 * c) <= slots) c <<= 1;      // small batch: spread a hypothesis over more SMs
-    if (n_hyp * (size_t)c > slots) c = std::max(c, PR_HYP_CLUSTER_BIG);        // large batch: see DESIGN.md 6.1 (measured)
+    // the smallest cluster that still fills the machine: n_hyp * C >= resident CTAs (a small batch spreads each
+    // hypothesis over more SMs), and never below 2 -- measured on 512 hypotheses x 22k points (592 resident CTAs):
+    // C = 1 1.60 ms, C = 2 1.45 ms, C = 4 1.54 ms: two CTAs per hypothesis halve what the claim counter hands out at the
+    // end of the launch, and the pairwise exchange is one st.async per lane
+    const size_t slots = (size_t)sms * (size_t)min_blocks;
+    int c = PR_HYP_CLUSTER_MIN;
+    while (c < kMaxCluster && n_hyp * (size_t)c < slots) c <<= 1;
     return c;
 }
 

@@ -214,6 +214,18 @@ def test_render_big_triangles_overflowing_bins(api, port, golden):
     assert np.array_equal(out.cpu().numpy(), want)
 
 
+def test_fast_division_is_exact(api, torch_mod):
+    """The rasteriser's division (refined reciprocal + residual correction, raster.cu) returns the bits of div.rn.f32:
+    2^26 pseudo-random quotients over the operand ranges the kernel guarantees (|b| in 2^-60..2^60, a = 0 or |a| in
+    2^-40..2^40), three seeds."""
+    from pose_refine_b200._lib import lib, check
+    import ctypes as C
+    out = torch_mod.zeros(1, dtype=torch_mod.int64, device="cuda")
+    for seed in (1, 2, 3):
+        check(lib().pr_debug_div_check(1 << 26, seed, out.data_ptr(), C.c_void_p(torch_mod.cuda.current_stream().cuda_stream)), "pr_debug_div_check")
+        assert int(out.item()) == 0, f"seed {seed}: {int(out.item())} quotients differ from div.rn.f32"
+
+
 def test_raw2depth_mask(api, port, fixture_scene, torch_mod):
     raw = fixture_scene["depth"].copy()
     raw[0, 0, :4] = [70000, -5, 65536, 1]
