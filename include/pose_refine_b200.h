@@ -232,6 +232,11 @@ int pr_scene_nn_build(const void* depth_dev, int depth_is_int32, uint32_t width,
 /* scene_pixels: width*height of the projective scene the workspace will be used with; for Scene_nn pass   */
 /* n_points + 2*n_nodes + 16 (room for the re-laid-out kd-tree; with less, the reference-layout walk is used). */
 size_t pr_icp_workspace_bytes(size_t n_hyp, size_t capacity_points, size_t scene_pixels);
+/* kd-tree scenes: the same plus one int per model point, in which every pass leaves the index of its nearest          */
+/* neighbour; the next pass starts its search from that point (the pose moves little between passes, so the walk only   */
+/* has to prove the candidate: 3-4x fewer node visits; the result is the same exact nearest neighbour).                 */
+/* pr_icp_nn_batch uses it when the workspace is at least this large.                                                   */
+size_t pr_icp_nn_workspace_bytes(size_t n_hyp, size_t capacity_points, size_t n_scene_points, size_t n_nodes);
 int pr_icp_projective_batch(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_dev, size_t n_hyp,
                             size_t capacity_points, const pr_scene_projective* scene, pr_icp_criteria criteria,
                             pr_registration_result* results_dev, int flags,
@@ -281,6 +286,10 @@ int pr_correspondences_projective(const float* pts_dev, size_t n, const pr_scene
 int pr_correspondences_nn(const float* pts_dev, size_t n, const pr_scene_nn* scene, int32_t* idx_dev,
                           void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
 int pr_solve_666_device(const float* S29_dev, size_t n, int fast, float* E16_dev, pr_stream_t stream);
+/*   pr_nn_walk_stats: cost of the packed kd-tree search over n queries: stats2_dev[0] = nodes fetched (box tests),    */
+/*                    stats2_dev[1] = leaf points tested (uint64 each).  For bench.py's C3 roofline block.               */
+int pr_nn_walk_stats(const float* pts_dev, size_t n, const pr_scene_nn* scene, uint64_t* stats2_dev,
+                     void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------- */
 /* pr_refiner: the whole path for one mesh + one scene behind a single call with HOST buffers -- */
@@ -315,6 +324,10 @@ int pr_refiner_run_device(pr_refiner* r, const float* poses_dev, size_t n_hyp, p
 /* the next run: depth (n_hyp*W*H int32), points, offsets (n_hyp+1), counts (n_hyp).              */
 int pr_refiner_buffers(pr_refiner* r, const int32_t** depth_dev, const float** pts_dev,
                        const uint32_t** offsets_dev, const uint32_t** counts_dev);
+/* ... and into the prepared scene (organised cloud + normals, W*H Vec3f each; kd-tree scenes: the leaf-ordered points)  */
+/* and the device copy of the results of the last pr_refiner_run (host variant).  Any pointer may be NULL.               */
+int pr_refiner_scene_buffers(pr_refiner* r, const float** scene_pcd_dev, const float** scene_normal_dev,
+                             const pr_registration_result** results_dev);
 /* kernel launches issued by this library since load (all entry points), for bench accounting.    */
 uint64_t pr_launch_count(void);
 

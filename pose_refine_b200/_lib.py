@@ -60,6 +60,7 @@ PROTOTYPES = {
     "pr_scene_nn_build_workspace_bytes": (_sz, [_u32, _u32]),
     "pr_scene_nn_build": (_i, [_vp, _i, _u32, _u32, _vp, _i, _vp, _vp, _sz, _vp, _sz, C.POINTER(_sz), C.POINTER(_sz), _vp, _sz, _vp]),
     "pr_icp_workspace_bytes": (_sz, [_sz, _sz, _sz]),
+    "pr_icp_nn_workspace_bytes": (_sz, [_sz, _sz, _sz, _sz]),
     "pr_icp_projective_batch": (_i, [_vp, _vp, _vp, _sz, _sz, C.POINTER(SceneProjective), Criteria, _vp, _i, _vp, _sz, _vp]),
     "pr_icp_nn_batch": (_i, [_vp, _vp, _vp, _sz, _sz, C.POINTER(SceneNN), Criteria, _vp, _i, _vp, _sz, _vp]),
     "pr_solve_666": (_i, [_vp, _vp, _vp]),
@@ -72,6 +73,7 @@ PROTOTYPES = {
     "pr_refiner_run": (_i, [_vp, _vp, _sz, Criteria, _vp, _vp]),
     "pr_refiner_run_device": (_i, [_vp, _vp, _sz, Criteria, _vp, _vp]),
     "pr_refiner_buffers": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "pr_refiner_scene_buffers": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "pr_launch_count": (C.c_uint64, []),
     "pr_debug_div_check": (_i, [C.c_uint64, _u32, _vp, _vp]),
     "pr_scene_projective_packed_bytes": (_sz, [_u32, _u32]),
@@ -82,6 +84,7 @@ PROTOTYPES = {
     "pr_correspondences_projective": (_i, [_vp, _sz, C.POINTER(SceneProjective), _vp, _vp, _sz, _vp]),
     "pr_correspondences_nn": (_i, [_vp, _sz, C.POINTER(SceneNN), _vp, _vp, _sz, _vp]),
     "pr_solve_666_device": (_i, [_vp, _sz, _i, _vp, _vp]),
+    "pr_nn_walk_stats": (_i, [_vp, _sz, C.POINTER(SceneNN), _vp, _vp, _sz, _vp]),
     "pr_refiner_set_scene_projective_device": (_i, [_vp, _vp, _i, _f, _vp]),
     "pr_refiner_set_scene_nn_device": (_i, [_vp, _vp, _i, _vp]),
     "pr_device_count": (_i, [C.POINTER(_i)]),

@@ -402,8 +402,10 @@ class SceneNN:
 # ---------------------------------------------------------------------------------------------
 # ICP
 def _icp_workspace(P, cap, scene):
-    n_px = scene.width * scene.height if isinstance(scene, SceneProjective) else scene.pcd.shape[0] + 2 * len(scene.nodes_host) + 16
-    ws_bytes = lib().pr_icp_workspace_bytes(P, cap, n_px)
+    if isinstance(scene, SceneProjective):
+        ws_bytes = lib().pr_icp_workspace_bytes(P, cap, scene.width * scene.height)
+    else:
+        ws_bytes = lib().pr_icp_nn_workspace_bytes(P, cap, scene.pcd.shape[0], len(scene.nodes_host))
     return torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device="cuda"), ws_bytes
 
 
@@ -566,6 +568,18 @@ class PoseRefiner:
         check(lib().pr_refiner_run_device(self._h, poses_dev.data_ptr(), P, criteria.c(), results_dev.data_ptr(), _stream()),
               "pr_refiner_run_device")
         return results_dev
+
+    def scene_buffers(self):
+        """Views of the prepared projective scene: (pcd [W*H,3], normal [W*H,3]) float32 on the device."""
+        p, n = C.c_void_p(), C.c_void_p()
+        check(lib().pr_refiner_scene_buffers(self._h, C.byref(p), C.byref(n), None), "pr_refiner_scene_buffers")
+        return _view(p.value, (self.width * self.height, 3), "<f4"), _view(n.value, (self.width * self.height, 3), "<f4")
+
+    def results_device(self, n_hyp):
+        """View of the device copy of the results the last run() (host variant) produced: [n_hyp, 18] float32."""
+        r = C.c_void_p()
+        check(lib().pr_refiner_scene_buffers(self._h, None, None, C.byref(r)), "pr_refiner_scene_buffers")
+        return _view(r.value, (n_hyp, 18), "<f4")
 
     def buffers(self, n_hyp):
         """Views of the refiner's own device buffers after a run of n_hyp hypotheses:

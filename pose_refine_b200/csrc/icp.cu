@@ -250,15 +250,8 @@ icp_pass_kernel(const float* __restrict__ pts, const uint32_t* __restrict__ offs
 #define PR_NN_WARPS 8
 #endif
 #ifndef PR_NN_MINB
-#define PR_NN_MINB 3
+#define PR_NN_MINB 4          // the tree walk hides latency with warps: 32 per SM at 64 registers (measured: 2 CTAs 141 ms, 3 124 ms, 4 112 ms on C3)
 #endif
-#ifndef PR_TILE_PTS
-#define PR_TILE_PTS 512
-#endif
-constexpr int kTilePts = PR_TILE_PTS;          // points per shared-memory tile (6 KB)
-constexpr int kTileBytes = kTilePts * 12;
-constexpr unsigned kSafePointOffset = 64 + 128;   // bytes from the CTA's state block to its spare point (0, 0, 1): behind T/state and the sums
-constexpr int kMaxStages = 16;                 // tiles per warp ring (wait parities are kept in a 32-bit mask)
 constexpr int kMaxCluster = 8;                 // portable cluster limit
 constexpr int kIlp = PR_HYP_ILP;               // points per lane per group of the projective loop (gathers in flight per lane)
 
@@ -564,20 +557,23 @@ __device__ __noinline__ float slow_slice(const PackedScene& s, const float* __re
     return warp_transpose_reduce(v);
 }
 
-// one tile, any scene with a per-point query() (nearest neighbour)
-template <class SceneT>
-__device__ __forceinline__ void compute_tile(const SceneT& s, unsigned tile, unsigned n, unsigned t_addr, AccT& acc, bool& odd) {
+// a warp's slice against the kd-tree: lane l takes points l, l + 32, ...  `cache` (nullable): one int per point of the
+// slice, the winner of the previous pass, which seeds this pass' search (nn_search_packed_t); pass 0 only writes it.
+__device__ __forceinline__ void compute_slice_nn(const PackedNnScene& s, const float* __restrict__ g, unsigned n, unsigned t_addr, AccT& acc,
+                                                 int* __restrict__ cache, bool use_cache) {
     const unsigned lane = threadIdx.x & 31;
-    (void)odd;
     float T[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) T[i] = lds32(t_addr + 4 * i);
 #pragma unroll 1
     for (unsigned i = lane; i < n; i += 32) {
         float px, py, pz;
-        transform(T, lds32(tile + 12 * i), lds32(tile + 12 * i + 4), lds32(tile + 12 * i + 8), px, py, pz);
+        transform(T, __ldg(g + 3 * i), __ldg(g + 3 * i + 1), __ldg(g + 3 * i + 2), px, py, pz);
         Corr c;
-        if (query(s, px, py, pz, c)) acc_add(acc, px, py, pz, c);
+        int found;
+        const int hint = (cache && use_cache) ? cache[i] : -1;
+        if (query(s, px, py, pz, c, hint, found)) acc_add(acc, px, py, pz, c);
+        if (cache) cache[i] = found;
     }
 }
 
@@ -594,11 +590,9 @@ template <class SceneT> struct HypTraits {
     using Acc = typename std::conditional<kProjective, AccP, AccT>::type;
     static constexpr size_t kExtraSmem = kProjective ? 0 : (size_t)kTopNodes * 32;     // top levels of the kd-tree
 };
-// dynamic shared memory of a CTA: state | sums | per-warp partials | cluster slots (2 parities) | mbarriers | tile rings
+// dynamic shared memory of a CTA: state | sums | spare | mbarriers | per-warp partials | cluster slots (2 parities) | tree top
 template <int kWarps> __host__ __device__ constexpr size_t hyp_fixed_smem() { return 64 + 128 + 64 + 64 + (size_t)kWarps * 128 + 2 * kMaxCluster * 128; }
-template <int kWarps> constexpr size_t hyp_smem(int n_stages, size_t extra) {
-    return hyp_fixed_smem<kWarps>() + (size_t)kWarps * (kMaxStages * 8) + extra + (size_t)kWarps * n_stages * kTileBytes;
-}
+template <int kWarps> constexpr size_t hyp_smem(size_t extra) { return hyp_fixed_smem<kWarps>() + extra; }
 
 // state words behind the 12 floats of T
 enum { kStFit = 12, kStRmse = 13, kStDone = 14, kStHyp = 15 };
@@ -631,48 +625,44 @@ __global__ void __launch_bounds__(HypTraits<SceneT>::kWarps * 32, HypTraits<Scen
 icp_hyp_kernel(const float* __restrict__ pts, size_t capacity_points, const uint32_t* __restrict__ offsets,
                const uint32_t* __restrict__ counts, unsigned n_hyp, HypCtl* ctl, float* __restrict__ final_T,
                SceneT scene, pr_icp_criteria crit, pr_registration_result* __restrict__ results,
-               float* __restrict__ out32, int n_stages) {
+               float* __restrict__ out32) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using Tr = HypTraits<SceneT>;
     constexpr int kWarps = Tr::kWarps;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned C = cluster_nctarank(), rank = cluster_ctarank();
-    // dynamic shared memory: state | sums | per-warp partials | cluster slots | mbarriers | tile rings
+    // dynamic shared memory: state | sums | spare point | mbarriers | per-warp partials | cluster slots | tree top
     float* s_T = reinterpret_cast<float*>(smem_raw);     // [12] T, then fitness, rmse, done, hypothesis id
     float* s_S = s_T + 16;                               // [32]: the hypothesis' sums of this pass
     float* s_safe = s_S + 32;                            // [3] the spare point (0, 0, 1) masked lanes read (+ padding to 64 bytes)
-    float* s_xbar = s_safe + 16;                         // two mbarriers (one per pass parity): the peers' partials have arrived
+    float* s_xbar = s_safe + 16;                         // three mbarriers: the peers' partials have arrived (one per pass parity), tree top copied
     float* s_part = s_xbar + 16;                         // [kWarps][32]
     float* s_cl = s_part + kWarps * 32;                  // [2][kMaxCluster][32]: CTA partials of the cluster, by pass parity
     volatile unsigned* s_w = reinterpret_cast<volatile unsigned*>(s_T);
     const unsigned smem0 = smem_u32(smem_raw);
-    const unsigned bar0 = smem0 + (unsigned)hyp_fixed_smem<kWarps>() + warp * (kMaxStages * 8);
-    const unsigned extra0 = smem0 + (unsigned)hyp_fixed_smem<kWarps>() + kWarps * (kMaxStages * 8);
-    const unsigned tile0 = extra0 + (unsigned)Tr::kExtraSmem + warp * (unsigned)n_stages * kTileBytes;
+    const unsigned extra0 = smem0 + (unsigned)hyp_fixed_smem<kWarps>();
     const uintptr_t pts_end = reinterpret_cast<uintptr_t>(pts) + capacity_points * 12;
 
     SceneT sc = scene;
     resolve_scene(sc);
     if (threadIdx.x < 3) s_safe[threadIdx.x] = (threadIdx.x == 2) ? 1.f : 0.f;
-    if (lane == 0) {
-        for (int s = 0; s < n_stages; s++) mbar_init(bar0 + 8 * s, 1);
-        if (warp == 0) { mbar_init(smem_u32(s_xbar), 1); mbar_init(smem_u32(s_xbar) + 8, 1); }
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(s_xbar), 1); mbar_init(smem_u32(s_xbar) + 8, 1); mbar_init(smem_u32(s_xbar) + 16, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
     unsigned xph = 0;                   // warp 0: bit p = parity to wait for on the exchange barrier of pass parity p
-    __syncwarp();
-    unsigned par = 0;                   // bit s = parity to wait for on stage s of this warp's ring
     if constexpr (!Tr::kProjective) {
         // kd-tree: nodes [0, n_top) = the top levels (breadth-first numbering) -> shared memory, one TMA bulk copy
         const int n_top = sc.nodes ? min(sc.n_nodes, kTopNodes) : 0;
         if (n_top > 0) {
             if (warp == 0) {
+                const unsigned tb = smem_u32(s_xbar) + 16;
                 if (lane == 0) {
-                    mbar_expect_tx(bar0, (unsigned)n_top * 32);
-                    tma_load_1d(extra0, sc.nodes, (unsigned)n_top * 32, bar0);
+                    mbar_expect_tx(tb, (unsigned)n_top * 32);
+                    tma_load_1d(extra0, sc.nodes, (unsigned)n_top * 32, tb);
                 }
-                mbar_wait(bar0, 0);
-                par ^= 1u;
+                mbar_wait(tb, 0);
             }
             sc.top = reinterpret_cast<const float4*>(smem_raw + (extra0 - smem0));
             sc.n_top = n_top;
@@ -708,42 +698,14 @@ icp_hyp_kernel(const float* __restrict__ pts, size_t capacity_points, const uint
         const unsigned first_pt = (g * ubase + min(g, urem)) << 6;
         const unsigned n_mine = my_units ? min(my_units << 6, n - first_pt) : 0u;
         const float* gsl = pts + 3 * ((size_t)offsets[h] + first_pt);
-        // ---- where the slice comes from.  Projective: straight from global memory, one group ahead, in registers
-        // (compute_slice).  Nearest neighbour: through the warp's ring of shared-memory tiles, filled by TMA.
+        // the slice is read straight from global memory every pass (L2-resident: nothing else touches those lines between
+        // the passes of a hypothesis): one group ahead in registers for the projective loop (compute_slice), point by
+        // point for the tree walk, whose cost per point is two orders of magnitude above the 12 bytes
         [[maybe_unused]] bool may_overread = false;
         if constexpr (Tr::kProjective) {
             constexpr unsigned kGroup = 32 * kIlp;
             may_overread = reinterpret_cast<uintptr_t>(gsl) + 12ull * (n_mine - n_mine % kGroup + 2 * kGroup) <= pts_end;
         }
-        const unsigned nt = Tr::kProjective ? 0u : (n_mine + kTilePts - 1) / kTilePts;
-        const bool resident = nt <= (unsigned)n_stages;          // the slice stays in shared memory for all passes
-        // TMA needs a 16-byte aligned source (offsets padded to 4 points give that) and a copy that, rounded up to 16
-        // bytes, stays inside the point buffer; otherwise the warp copies its tiles with plain loads
-        const bool use_tma = ((reinterpret_cast<uintptr_t>(gsl) & 15) == 0) &&
-                             (reinterpret_cast<uintptr_t>(gsl) + ((n_mine * 12 + 15) & ~15u) <= pts_end);
-        unsigned to_issue = resident ? nt : nt * (unsigned)(crit.max_iteration + 1);     // tile loads still to issue
-        unsigned in_flight = 0;                 // tile loads issued and not yet waited for
-        unsigned itile = 0, istage = 0;         // tile and stage of the next load
-        unsigned cstage = 0;                    // stage of the next tile to consume (streaming)
-        auto issue_one = [&]() {
-            const unsigned np = min((unsigned)kTilePts, n_mine - itile * kTilePts);
-            const float* src = gsl + (size_t)itile * (kTilePts * 3);
-            const unsigned dst = tile0 + istage * kTileBytes;
-            if (use_tma) {
-                if (lane == 0) {
-                    const unsigned bytes = (np * 12 + 15) & ~15u;
-                    mbar_expect_tx(bar0 + 8 * istage, bytes);
-                    tma_load_1d(dst, src, bytes, bar0 + 8 * istage);
-                }
-            } else {
-                for (unsigned i = lane; i < np * 3; i += 32) sts32(dst + 4 * i, src[i]);
-                __syncwarp();
-            }
-            itile = (itile + 1 == nt) ? 0 : itile + 1;
-            istage = (istage + 1 == (unsigned)n_stages) ? 0 : istage + 1;
-            to_issue--; in_flight++;
-        };
-        for (unsigned k = min((unsigned)n_stages, to_issue); k; k--) issue_one();
 
         for (int pass = 0;; pass++) {
             const unsigned t_addr = smem_u32(s_T);
@@ -751,23 +713,7 @@ icp_hyp_kernel(const float* __restrict__ pts, size_t capacity_points, const uint
             acc_zero(acc);
             bool odd = false;
             if constexpr (Tr::kProjective) compute_slice(sc, gsl, n_mine, may_overread, t_addr, acc, odd);
-            for (unsigned t = 0; t < nt; t++) {
-                const unsigned stage = resident ? t : cstage;
-                if (!resident || pass == 0) {
-                    if (use_tma) {
-                        mbar_wait(bar0 + 8 * stage, (par >> stage) & 1u);
-                        par ^= (1u << stage);
-                    }
-                    in_flight--;
-                }
-                if constexpr (!Tr::kProjective)
-                    compute_tile(sc, tile0 + stage * kTileBytes, min((unsigned)kTilePts, n_mine - t * kTilePts), t_addr, acc, odd);
-                if (!resident) {
-                    __syncwarp();            // every lane is done reading this stage before it is refilled
-                    if (to_issue) issue_one();
-                    cstage = (cstage + 1 == (unsigned)n_stages) ? 0 : cstage + 1;
-                }
-            }
+            else compute_slice_nn(sc, gsl, n_mine, t_addr, acc, sc.cache ? sc.cache + ((size_t)offsets[h] + first_pt) : nullptr, pass > 0);
             // ---- the warp's 29 sums -> lane l holds sum l
             float v[32];
             acc_unpack(acc, v);
@@ -810,16 +756,6 @@ icp_hyp_kernel(const float* __restrict__ pts, size_t capacity_points, const uint
             __syncthreads();
             if (s_w[kStDone]) break;
         }
-        // ---- loads issued ahead of a pass that never ran: wait for them before the ring is reused
-        while (in_flight) {
-            if (use_tma) {
-                mbar_wait(bar0 + 8 * cstage, (par >> cstage) & 1u);
-                par ^= (1u << cstage);
-            }
-            in_flight--;
-            cstage = (cstage + 1 == (unsigned)n_stages) ? 0 : cstage + 1;
-        }
-        __syncwarp();
     }
 }
 
@@ -894,6 +830,16 @@ corr_nn_kernel(const float* __restrict__ pts, unsigned n, PackedNnScene s, int* 
     out_idx[i] = b < 0 ? -1 : b;
 }
 
+// node fetches (box tests) and leaf-point distance tests of the packed walk, summed over the queries
+__global__ void __launch_bounds__(256)
+walk_stats_kernel(const float* __restrict__ pts, unsigned n, PackedNnScene s, unsigned long long* __restrict__ stats) {
+    const unsigned i = blockIdx.x * 256 + threadIdx.x;
+    unsigned v = 0, t = 0;
+    if (i < n) nn_search_packed_t<true>(s, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], v, t);
+    v = __reduce_add_sync(0xffffffffu, v); t = __reduce_add_sync(0xffffffffu, t);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(stats, (unsigned long long)v); atomicAdd(stats + 1, (unsigned long long)t); }
+}
+
 __global__ void __launch_bounds__(64)
 solve_kernel(const float* __restrict__ S29, unsigned n, int fast, float* __restrict__ E16) {
     const unsigned i = blockIdx.x * 64 + threadIdx.x;
@@ -910,6 +856,7 @@ inline size_t icp_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct IcpWs {
     HypState* state; uint32_t* chunk_hyp; HypCtl* ctl; uint32_t* total_chunks; float* partials; float* final_T; float4* packed;
+    int* nn_cache;       // capacity_points ints (kd-tree scenes, optional)
     size_t max_chunks, bytes;
 };
 
@@ -921,7 +868,7 @@ inline uint32_t pick_chunk_points(size_t n_hyp, size_t capacity_points, int sms)
     return chunk;
 }
 
-inline IcpWs carve_icp_ws(void* base, size_t n_hyp, size_t capacity_points, size_t scene_pixels) {
+inline IcpWs carve_icp_ws(void* base, size_t n_hyp, size_t capacity_points, size_t scene_pixels, bool with_nn_cache = false) {
     IcpWs ws;
     ws.max_chunks = capacity_points / 512 + n_hyp + 1;      // sized for the smallest chunk the per-pass driver uses
     char* w = (char*)base;
@@ -934,6 +881,7 @@ inline IcpWs carve_icp_ws(void* base, size_t n_hyp, size_t capacity_points, size
     ws.partials = (float*)take(ws.max_chunks * kPartialStride * 4);
     ws.final_T = (float*)take(n_hyp * 12 * 4);
     ws.packed = (float4*)take(scene_pixels * 32);
+    ws.nn_cache = with_nn_cache ? (int*)take(capacity_points * 4 + 256) : nullptr;
     ws.bytes = used;
     return ws;
 }
@@ -979,6 +927,14 @@ inline int pick_cluster(size_t n_hyp, int sms, int min_blocks) {
     return c;
 }
 
+// kd-tree scenes: the same rule (measured on C3: C = 2 112 ms, 4 113 ms, 8 116 ms)
+inline int pick_cluster_nn(size_t n_hyp, int sms, int min_blocks) {
+#ifdef PR_DEBUG
+    if (const char* e = getenv("PR_NN_CLUSTER")) { const int c = atoi(e); if (c == 1 || c == 2 || c == 4 || c == 8) return c; }
+#endif
+    return pick_cluster(n_hyp, sms, min_blocks);
+}
+
 template <class SceneT>
 int launch_hyp(const float* pts_dev, size_t capacity_points, const uint32_t* offsets_dev, const uint32_t* counts_dev, size_t n_hyp,
                const IcpWs& ws, const SceneT& scene, pr_icp_criteria crit, pr_registration_result* results_dev, float* out32,
@@ -988,15 +944,10 @@ int launch_hyp(const float* pts_dev, size_t capacity_points, const uint32_t* off
     DeviceInfo di;
     int rc = device_info(di);
     if (rc != PR_OK) return rc;
-    // tile ring: as many stages as fit next to kMinBlocks - 1 other CTAs (1 KB per CTA is reserved by the system)
-    const size_t sm_total = 233472;      // 228 KB of shared memory per SM
-    size_t budget = std::min(di.smem_optin, sm_total / (size_t)Tr::kMinBlocks - 1024);
-    int n_stages = (int)((budget - hyp_smem<Tr::kWarps>(0, Tr::kExtraSmem)) / ((size_t)Tr::kWarps * kTileBytes));
-    n_stages = Tr::kProjective ? 0 : std::max(2, std::min(kMaxStages, n_stages));
-    const size_t smem = hyp_smem<Tr::kWarps>(n_stages, Tr::kExtraSmem);
+    const size_t smem = hyp_smem<Tr::kWarps>(Tr::kExtraSmem);
     auto kernel = icp_hyp_kernel<SceneT>;
     PR_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int C = pick_cluster(n_hyp, di.sms, Tr::kMinBlocks);
+    const int C = Tr::kProjective ? pick_cluster(n_hyp, di.sms, Tr::kMinBlocks) : pick_cluster_nn(n_hyp, di.sms, Tr::kMinBlocks);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cudaLaunchAttribute attr[1];
@@ -1030,7 +981,7 @@ int launch_hyp(const float* pts_dev, size_t capacity_points, const uint32_t* off
     HypCtl* ctl = ws.ctl;
     float* final_T = ws.final_T;
     PR_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, pts_dev, capacity_points, offsets_dev, counts_dev, n_hyp_u, ctl, final_T, scene, crit,
-                                   results_dev, out32, n_stages));
+                                   results_dev, out32));
     count_launch();
     return PR_OK;
 }
@@ -1160,6 +1111,10 @@ size_t pr_icp_workspace_bytes(size_t n_hyp, size_t capacity_points, size_t scene
     return carve_icp_ws(nullptr, n_hyp, capacity_points, scene_pixels).bytes;
 }
 
+size_t pr_icp_nn_workspace_bytes(size_t n_hyp, size_t capacity_points, size_t n_scene_points, size_t n_nodes) {
+    return carve_icp_ws(nullptr, n_hyp, capacity_points, n_scene_points + 2 * n_nodes + 16, true).bytes;
+}
+
 size_t pr_scene_projective_packed_bytes(uint32_t width, uint32_t height) { return (size_t)width * height * 32; }
 
 int pr_scene_projective_pack(const pr_scene_projective* scene, void* packed_dev, pr_stream_t stream) {
@@ -1222,16 +1177,19 @@ int pr_icp_nn_batch(float* pts_dev, const uint32_t* offsets_dev, const uint32_t*
     // together); a foreign tree that does is detected by the packing kernel, which then marks the packed root as an empty
     // leaf-less tree and the kernel walks the reference layout instead -- decided on the device, no host round trip.
     const size_t units = scene->n_points + 2 * scene->n_nodes + 16;
-    const IcpWs ws = carve_icp_ws(workspace_dev, n_hyp, capacity_points, units);
+    // with room for one int per model point (pr_icp_nn_workspace_bytes) every pass starts its searches from the previous
+    // pass' winners; a workspace sized by pr_icp_workspace_bytes still works, without that
+    IcpWs ws = carve_icp_ws(workspace_dev, n_hyp, capacity_points, units, true);
+    if (workspace_bytes < ws.bytes) ws = carve_icp_ws(workspace_dev, n_hyp, capacity_points, units, false);
     if (workspace_bytes < ws.bytes) return PR_ERR_WORKSPACE_TOO_SMALL;
     PackedNnScene ps;
     ps.max_dist_sq = s.max_dist_sq; ps.nrm = s.nrm; ps.n_nodes = s.n_nodes; ps.ref = s;
-    ps.nodes = nullptr; ps.pts4 = nullptr; ps.unsupported = nullptr; ps.top = nullptr; ps.n_top = 0;
+    ps.nodes = nullptr; ps.pts4 = nullptr; ps.unsupported = nullptr; ps.top = nullptr; ps.n_top = 0; ps.cache = nullptr;
     if (!(flags & PR_ICP_REFERENCE_ARITHMETIC) && s.n_nodes > 0) {
         const PackedTree t = carve_packed_tree(ws.packed, scene->n_points, scene->n_nodes);
         rc = pack_tree(s, scene->n_points, t, stream);
         if (rc != PR_OK) return rc;
-        ps.nodes = t.nodes; ps.pts4 = t.pts4; ps.unsupported = t.flag;
+        ps.nodes = t.nodes; ps.pts4 = t.pts4; ps.unsupported = t.flag; ps.cache = ws.nn_cache;
     }
     return run_icp(pts_dev, offsets_dev, counts_dev, n_hyp, capacity_points, s, ps, criteria, results_dev, flags, ws, stream);
 }
@@ -1295,7 +1253,7 @@ int pr_pass_sums_nn(const float* pts_dev, const uint32_t* offsets_dev, const uin
     cudaStream_t stream = as_stream(stream_);
     PackedNnScene ps;
     ps.max_dist_sq = s.max_dist_sq; ps.nrm = s.nrm; ps.n_nodes = s.n_nodes; ps.ref = s;
-    ps.nodes = nullptr; ps.pts4 = nullptr; ps.unsupported = nullptr; ps.top = nullptr; ps.n_top = 0;
+    ps.nodes = nullptr; ps.pts4 = nullptr; ps.unsupported = nullptr; ps.top = nullptr; ps.n_top = 0; ps.cache = nullptr;
     if (s.n_nodes > 0) {
         const PackedTree t = carve_packed_tree(ws.packed, scene->n_points, scene->n_nodes);
         rc = pack_tree(s, scene->n_points, t, stream);
@@ -1344,8 +1302,32 @@ int pr_correspondences_nn(const float* pts_dev, size_t n, const pr_scene_nn* sce
     if (rc != PR_OK) return rc;
     PackedNnScene ps;
     ps.max_dist_sq = s.max_dist_sq; ps.nrm = s.nrm; ps.n_nodes = s.n_nodes; ps.ref = s;
-    ps.nodes = t.nodes; ps.pts4 = t.pts4; ps.unsupported = t.flag; ps.top = nullptr; ps.n_top = 0;
+    ps.nodes = t.nodes; ps.pts4 = t.pts4; ps.unsupported = t.flag; ps.top = nullptr; ps.n_top = 0; ps.cache = nullptr;
     corr_nn_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pts_dev, (unsigned)n, ps, idx_dev);
+    count_launch();
+    PR_LAUNCH_CHECK();
+    return PR_OK;
+}
+
+int pr_nn_walk_stats(const float* pts_dev, size_t n, const pr_scene_nn* scene, uint64_t* stats2_dev,
+                     void* workspace_dev, size_t workspace_bytes, pr_stream_t stream_) {
+    NnScene s;
+    int rc = make_nn_scene(scene, s);
+    if (rc != PR_OK) return rc;
+    if (!pts_dev || !stats2_dev || !workspace_dev || n > 0x7FFFFFFFull || s.n_nodes == 0) return PR_ERR_INVALID_ARGUMENT;
+    cudaStream_t stream = as_stream(stream_);
+    PR_CUDA_TRY(cudaMemsetAsync(stats2_dev, 0, 16, stream));
+    if (n == 0) return PR_OK;
+    const size_t units = scene->n_points + 2 * scene->n_nodes + 16;
+    IcpWs ws = carve_icp_ws(workspace_dev, 1, n, units);
+    if (workspace_bytes < ws.bytes) return PR_ERR_WORKSPACE_TOO_SMALL;
+    const PackedTree t = carve_packed_tree(ws.packed, scene->n_points, scene->n_nodes);
+    rc = pack_tree(s, scene->n_points, t, stream);
+    if (rc != PR_OK) return rc;
+    PackedNnScene ps;
+    ps.max_dist_sq = s.max_dist_sq; ps.nrm = s.nrm; ps.n_nodes = s.n_nodes; ps.ref = s;
+    ps.nodes = t.nodes; ps.pts4 = t.pts4; ps.unsupported = t.flag; ps.top = nullptr; ps.n_top = 0; ps.cache = nullptr;
+    walk_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pts_dev, (unsigned)n, ps, reinterpret_cast<unsigned long long*>(stats2_dev));
     count_launch();
     PR_LAUNCH_CHECK();
     return PR_OK;

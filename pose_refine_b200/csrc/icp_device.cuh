@@ -125,19 +125,26 @@ __device__ __forceinline__ bool query(const NnScene& s, float px, float py, floa
 // build_tree numbers the nodes generation by generation (breadth first), so nodes [0, kTopNodes) ARE the top levels
 // of the tree: the kernel keeps them in shared memory (one TMA bulk copy per CTA), deeper nodes come through L1/L2.
 //
-// The query is an exact nearest-neighbour search that returns the SAME point as Scene_nn::query, ties included:
-//   * same visiting order: at an internal node the child on the query's side of the split plane first
-//     (pcd_scene.h:92-100), the other one afterwards; leaves scan [left, right) in order;
-//   * same update rule: strict <, so among points at exactly the minimum distance the first one visited wins
-//     (pcd_scene.h:88-90);
-//   * pruning never removes that winner: a subtree is skipped only when the distance to the box of its own points,
-//     scaled by 0.99999 (the bound is a rounded float), is >= the best distance so far -- a point that is at least as
-//     near as the current best is strictly inside that margin.  The reference prunes with the box of the node it
-//     RE-VISITS (much weaker: 385 node visits per query on the fixture vs ~20-40 here); both
-//     walks visit the winner's leaf, in the same relative order.
-// It starts from best = max_dist^2 (anything farther is invalid anyway, pcd_scene.h:127) and parks the far children
-// (ids only; the bound is recomputed from the box when the node is fetched) on a small explicit stack.
-constexpr int kTopNodes = 512;            // 16 KB of shared memory: the top 9 levels
+// The query is an exact nearest-neighbour search that returns the SAME point as Scene_nn::query, ties included.
+// It descends into the child whose box is nearer first (that finds a good candidate early, which is what makes the
+// pruning bite: the reference's own order -- the query's side of the split plane first -- needs 2-3x the node visits
+// on thin-shell scenes when the query is still a few centimetres off the surface), prunes a subtree when the distance
+// to the box of its OWN points, scaled by 0.99999 (the bound is a rounded float), is >= the best distance so far, and
+// keeps the candidate on strict <.  None of that can change WHICH point wins unless two points are at exactly the same
+// float distance; the reference then keeps the one its own walk visits first (strict <, pcd_scene.h:88-90).  So on
+// d2 == best the two candidates are put in the reference's visiting order explicitly (nn_visited_first: walk down
+// from the root to the node where their index ranges part; the child on the query's side of the split plane is
+// visited first, pcd_scene.h:92-100; inside a leaf the lower index).  A subtree that holds a point at exactly the best
+// distance is never pruned (its bound is <= that distance, strictly below it after the margin), so every tie is seen.
+// The search starts from best = max_dist^2 (anything farther is invalid anyway, pcd_scene.h:127) and parks the far
+// children whose box is still within reach (id + bound) on a small explicit stack.
+// Measured on C3 (512 hypotheses, 99k-point tree, 4 CTAs per SM): 512 nodes staged 155 ms, 128 nodes 145 ms, 16 nodes 107 ms
+// per step, none 136 ms (before the search cache) -- the walk lives in L1, every CTA of an SM would hold its own copy of the
+// same top levels, and L1 already keeps ONE copy of them hot; beyond the first levels staging only takes L1 away.
+#ifndef PR_NN_TOP
+#define PR_NN_TOP 16
+#endif
+constexpr int kTopNodes = PR_NN_TOP;      // the top 4 levels (15 nodes), 512 bytes of shared memory per CTA
 struct PackedNnScene {
     float max_dist_sq;
     const float4* nodes;      // 2 per node
@@ -147,6 +154,7 @@ struct PackedNnScene {
     const unsigned* unsupported;   // device flag raised by nn_pack_nodes_kernel: this tree does not fit the encoding
     const float4* top;        // shared-memory copy of nodes [0, n_top) (set by the kernel; nullptr: none)
     int n_top;
+    int* cache;               // one int per model point of the batch (same indexing as the points): last pass' winner; nullable
     NnScene ref;              // the reference layout (fallback walk when the stack would overflow)
 };
 
@@ -189,54 +197,116 @@ __device__ __forceinline__ float box_dist_sq(const float4& lo, const float4& hi,
     const float dz = fmaxf(fmaxf(lo.z - pz, pz - hi.z), 0.f);
     return dx * dx + dy * dy + dz * dz;
 }
-// node i of the packed tree: top levels from shared memory, the rest through the read-only path
-__device__ __forceinline__ void load_node(const PackedNnScene& s, int i, float4& lo, float4& hi) {
-    if (i < s.n_top) { lo = s.top[2 * i]; hi = s.top[2 * i + 1]; }
-    else { lo = __ldg(s.nodes + 2 * i); hi = __ldg(s.nodes + 2 * i + 1); }
+// children (c, c + 1) of an internal node: four consecutive float4 = one 64-byte fetch.  The top levels come from the
+// CTA's shared-memory copy, deeper nodes through L1/L2; the pointer is SELECTED (not branched on), and the loads are
+// generic, so lanes of a warp that are at different depths do not diverge here.
+__device__ __forceinline__ const float4* node_ptr(const PackedNnScene& s, int i) {
+    return (i + 1 < s.n_top) ? s.top + 2 * i : s.nodes + 2 * i;
+}
+
+// true when Scene_nn::query's walk reaches point a before point b (a != b) for this query
+__device__ __noinline__ bool nn_visited_first(const NnScene& s, float px, float py, float pz, int a, int b) {
+    int cur = 0;
+    for (;;) {
+        const pr_node_kdtree* nd = s.nodes + cur;
+        const int c1 = nd->child1, c2 = nd->child2;
+        if (c1 < 0 || c2 < 0) return a < b;                                   // same leaf: scanned in index order
+        const int mid = s.nodes[c2].left;                                     // child1 owns [left, mid), child2 [mid, right)
+        const bool a1 = a < mid, b1 = b < mid;
+        if (a1 == b1) { cur = a1 ? c1 : c2; continue; }
+        const int dim = nd->split_dim;
+        const float diff = (dim == 0 ? px : (dim == 1 ? py : pz)) - nd->split_v;
+        return (diff < 0.f) ? a1 : !a1;                                       // the query's side first (pcd_scene.h:92-100)
+    }
 }
 
 // exact nearest neighbour over the packed tree: index of the winner (leaf order), or -1 when nothing is nearer
 // than max_dist.  -2: the explicit stack overflowed (the caller falls back to the reference walk).
-__device__ __forceinline__ int nn_search_packed(const PackedNnScene& s, float px, float py, float pz) {
+// hint: a scene point to start from (>= 0), typically the winner of the previous ICP pass of the same model point -- the
+// pose moves little between passes, so its distance is already (nearly) the minimum and the walk only has to prove it:
+// every subtree farther than that is pruned at once.  The result does not depend on the hint (it is just a candidate
+// "visited" early; ties are ordered by nn_visited_first, not by visiting order).
+template <bool COUNT>
+__device__ __forceinline__ int nn_search_packed_t(const PackedNnScene& s, float px, float py, float pz, unsigned& visits, unsigned& tests,
+                                                  int hint = -1) {
     if (s.n_nodes <= 0) return -1;
     constexpr int kStack = 24;       // far children parked: one per level at most (trees here are <= 20 deep)
     int stack_n[kStack];
+    float stack_lb[kStack];
     int sp = 0;
     float best = s.max_dist_sq;
     int best_i = -1;
+    if (hint >= 0) {
+        const float4 q = __ldg(s.pts4 + hint);
+        const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+        const float d2 = addf(addf(mulf(dx, dx), mulf(dy, dy)), mulf(dz, dz));
+        if (d2 < best) { best = d2; best_i = hint; }
+    }
     bool overflow = false;
     float4 lo, hi;
-    load_node(s, 0, lo, hi);
+    { const float4* p = node_ptr(s, 0); lo = p[0]; hi = p[1]; }
+    if (COUNT) visits++;
+    // a box lower bound is a rounded float, so it is trusted only with a 1e-5 margin
     bool go = box_dist_sq(lo, hi, px, py, pz) * 0.99999f < best;
     while (go) {
         const int a = __float_as_int(lo.w);
         if (a < 0) {
             const int left = a & 0xFFFFFF, cnt = (a >> 24) & 127;
+            if (COUNT) tests += (unsigned)cnt;
             for (int i = left; i < left + cnt; i++) {
                 const float4 q = __ldg(s.pts4 + i);
                 const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
                 const float d2 = addf(addf(mulf(dx, dx), mulf(dy, dy)), mulf(dz, dz));    // pcd_scene.h:86-89
                 if (d2 < best) { best = d2; best_i = i; }
+                else if (d2 == best && best_i >= 0 && i != best_i && nn_visited_first(s.ref, px, py, pz, i, best_i)) best_i = i;
             }
             go = false;
         } else {
-            const int dim = a >> 28, c1 = a & 0xFFFFFFF;
-            const float diff = (dim == 0 ? px : (dim == 1 ? py : pz)) - hi.w;            // pcd_scene.h:92-95
-            const int near_c = (diff < 0.f) ? c1 : c1 + 1, far_c = (diff < 0.f) ? c1 + 1 : c1;
-            if (sp < kStack) stack_n[sp++] = far_c; else overflow = true;
-            load_node(s, near_c, lo, hi);
-            if (box_dist_sq(lo, hi, px, py, pz) * 0.99999f < best) continue;
+            const int c1 = a & 0xFFFFFFF;
+            const float4* p = node_ptr(s, c1);
+            const float4 lo1 = p[0], hi1 = p[1], lo2 = p[2], hi2 = p[3];
+            if (COUNT) visits += 2;
+            const float lb1 = box_dist_sq(lo1, hi1, px, py, pz) * 0.99999f, lb2 = box_dist_sq(lo2, hi2, px, py, pz) * 0.99999f;
+            const bool first1 = lb1 <= lb2;          // the nearer box first
+            const float lb_near = first1 ? lb1 : lb2, lb_far = first1 ? lb2 : lb1;
+            if (lb_far < best) {
+                if (sp < kStack) { stack_n[sp] = first1 ? c1 + 1 : c1; stack_lb[sp] = lb_far; sp++; }
+                else overflow = true;
+            }
+            if (lb_near < best) { lo = first1 ? lo1 : lo2; hi = first1 ? hi1 : hi2; continue; }
             go = false;
         }
         while (sp > 0) {
-            const int n = stack_n[--sp];
-            load_node(s, n, lo, hi);
-            if (box_dist_sq(lo, hi, px, py, pz) * 0.99999f < best) { go = true; break; }
+            --sp;
+            if (stack_lb[sp] < best) {
+                const float4* p = (stack_n[sp] < s.n_top) ? s.top + 2 * stack_n[sp] : s.nodes + 2 * stack_n[sp];
+                lo = p[0]; hi = p[1];
+                go = true;
+                break;
+            }
         }
     }
     return overflow ? -2 : best_i;
 }
+__device__ __forceinline__ int nn_search_packed(const PackedNnScene& s, float px, float py, float pz) {
+    unsigned v = 0, t = 0;
+    return nn_search_packed_t<false>(s, px, py, pz, v, t);
+}
 
+// hint / found: see nn_search_packed_t; found = -1 when there is no valid correspondence
+__device__ __forceinline__ bool query(const PackedNnScene& s, float px, float py, float pz, Corr& c, int hint, int& found) {
+    found = -1;
+    if (s.nodes == nullptr) return query(s.ref, px, py, pz, c);
+    unsigned v = 0, t = 0;
+    const int best_i = nn_search_packed_t<false>(s, px, py, pz, v, t, hint);
+    if (best_i == -2) return query(s.ref, px, py, pz, c);     // deeper than the stack: the reference walk
+    if (best_i < 0) return false;
+    found = best_i;
+    const float4 q = __ldg(s.pts4 + best_i);
+    c.qx = q.x; c.qy = q.y; c.qz = q.z;
+    c.nx = __ldg(s.nrm + 3 * best_i); c.ny = __ldg(s.nrm + 3 * best_i + 1); c.nz = __ldg(s.nrm + 3 * best_i + 2);
+    return true;
+}
 __device__ __forceinline__ bool query(const PackedNnScene& s, float px, float py, float pz, Corr& c) {
     if (s.nodes == nullptr) return query(s.ref, px, py, pz, c);
     const int best_i = nn_search_packed(s, px, py, pz);

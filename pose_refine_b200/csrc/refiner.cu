@@ -244,6 +244,15 @@ int pr_refiner_set_scene_nn_device(pr_refiner* r, const void* depth_dev, int dep
     rc = pr_scene_nn_build(depth_dev, depth_is_int32, r->W, r->H, r->K, 10, r->d_scene_pcd, r->d_scene_nrm, n_px, r->d_nodes,
                            2 * n_px + 1, &n_pts, &n_nodes, r->d_scene_ws, r->scene_ws_bytes, stream);
     if (rc != PR_OK) return rc;
+    {   // room for the nearest-neighbour cache (one int per model point): grow the ICP workspace once
+        const size_t need = pr_icp_nn_workspace_bytes(r->max_hyp, r->capacity_points, n_pts, n_nodes);
+        if (need > r->ws_icp_bytes) {
+            PR_CUDA_TRY(cudaStreamSynchronize(prb::as_stream(stream)));
+            cudaFree(r->ws_icp); r->ws_icp = nullptr; r->ws_icp_bytes = 0;
+            PR_CUDA_TRY(cudaMalloc(&r->ws_icp, need));
+            r->ws_icp_bytes = need;
+        }
+    }
     r->sn.max_dist_diff = 0.1f;   // Scene_nn has no setter upstream (pcd_scene.h:49)
     r->sn.pcd_dev = r->d_scene_pcd; r->sn.normal_dev = r->d_scene_nrm; r->sn.nodes_dev = r->d_nodes;
     r->sn.n_points = n_pts; r->sn.n_nodes = n_nodes;
@@ -288,6 +297,15 @@ int pr_refiner_buffers(pr_refiner* r, const int32_t** depth_dev, const float** p
     if (pts_dev) *pts_dev = r->d_pts;
     if (offsets_dev) *offsets_dev = r->d_offsets;
     if (counts_dev) *counts_dev = r->d_counts;
+    return PR_OK;
+}
+
+int pr_refiner_scene_buffers(pr_refiner* r, const float** scene_pcd_dev, const float** scene_normal_dev,
+                             const pr_registration_result** results_dev) {
+    if (!r) return PR_ERR_INVALID_ARGUMENT;
+    if (scene_pcd_dev) *scene_pcd_dev = r->d_scene_pcd;
+    if (scene_normal_dev) *scene_normal_dev = r->d_scene_nrm;
+    if (results_dev) *results_dev = r->d_results;
     return PR_OK;
 }
 

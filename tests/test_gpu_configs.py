@@ -87,7 +87,15 @@ def test_c3_kdtree_scene_100k(api, port, mesh, fixture_scene, golden):
         want = port.icp(pn, h_pts[h_off[i]: h_off[i] + h_cnt[i]], 0.0, 0.0, 30)["raw"]
         assert_result_close(res[i], want, f"C3 hyp {i}")
     port.set_threads(1)
-    # the packed-tree search returns the reference walk's nearest neighbour: one pass of sums agrees
-    got = api.pcd2ab(h_pts[: h_cnt[0]], scene).astype(np.float64)
+    # one pass of sums through both kernels: the reference-arithmetic one (its stackless walk) and the shipped one
+    # (packed tree, child-box pruning) count the same inliers as the oracle on this 100k-point tree
     ref = port.pcd2ab(pn, h_pts[: h_cnt[0]]).astype(np.float64)
+    got = api.pcd2ab(h_pts[: h_cnt[0]], scene).astype(np.float64)
     assert got[28] == ref[28]
+    shipped = api.pass_sums(pts, offsets, counts, scene).astype(np.float64)
+    assert shipped[0, 28] == ref[28]
+    from test_gpu_parity import _terms_f64
+    q, n, valid = port.query(pn, h_pts[: h_cnt[0]])
+    terms = _terms_f64(h_pts[: h_cnt[0]], q, n, valid)
+    truth, mag = terms.sum(0), np.abs(terms).sum(0)
+    assert np.all(np.abs(shipped[0] - truth) <= 2e-6 * mag + 1e-30)
