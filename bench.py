@@ -219,6 +219,27 @@ def run_ours(args):
         barrier()
         return max_over_ranks(e0.elapsed_time(e1))
 
+    def median_step(step, steps, warmup, after=None):
+        """the extra configurations: one CUDA event pair per step, MEDIAN over the steps (a shared host now and then stalls
+        a single launch several-fold), max over ranks (ms per step)"""
+        for _ in range(warmup):
+            step()
+        if after:
+            after()
+        barrier()
+        ts = []
+        for _ in range(steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            if after:
+                after()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        barrier()
+        return max_over_ranks(float(np.median(ts)))
+
     def scene_on_every_rank(mesh, scene_pose, w, h, proj):
         """rank 0 renders the scene; pr_broadcast_scene (NCCL, device to device) hands it to the others"""
         if rank == 0:
@@ -342,7 +363,7 @@ def run_ours(args):
     configs = None
     if not args.no_configs:
         configs = {}
-        ksteps = max(2, min(args.steps, 5))
+        ksteps = max(3, min(args.steps, 7))
 
         # ---- C3: kd-tree scene of ~100k points, 512 hypotheses per GPU (weak)
         chk_scene = scene_depth.cpu().numpy()
@@ -350,7 +371,7 @@ def run_ours(args):
         r3 = api.PoseRefiner(mesh, W, H, K, max_hyp=P)
         r3.set_scene_nn_device(c3_depth)
         res3 = torch.empty((P, 18), dtype=torch.float32, device="cuda")
-        ms3 = timed_loop(lambda: r3.run_device(poses_dev, crit, res3), ksteps, 1) / ksteps
+        ms3 = median_step(lambda: r3.run_device(poses_dev, crit, res3), ksteps, 1)
         if rank == 0:
             _, pts3, off3, cnt3 = r3.buffers(P)
             n3 = int(cnt3.sum().item())
@@ -398,7 +419,7 @@ def run_ours(args):
             gat4[: len(poses4)].copy_(res4)
             comm.gather_results(gat4, all4)
 
-        ms4 = timed_loop(step4, ksteps, 1, after=lambda: comm.wait()) / ksteps
+        ms4 = median_step(step4, ksteps, 1, after=lambda: comm.wait())
         if rank == 0:
             nb = min(chunk, len(poses4))
             r4.run_device(p4_dev[:nb], crit, res4[:nb])
@@ -424,7 +445,7 @@ def run_ours(args):
         cl5 = (torch.as_tensor(off5).cuda(), torch.as_tensor(cv5).cuda())
         depth5 = torch.empty((n5, H, W), dtype=torch.int32, device="cuda")
         ws5 = torch.empty(L.pr_render_cloud_workspace_bytes(n5, verts5.shape[0], faces5.shape[0], W, H), dtype=torch.uint8, device="cuda")
-        ms5 = timed_loop(lambda: api.render_clustered_keep_in_gpu(v5, f5, p5, W, H, proj, cl5, out=depth5, ws=ws5), ksteps, 1) / ksteps
+        ms5 = median_step(lambda: api.render_clustered_keep_in_gpu(v5, f5, p5, W, H, proj, cl5, out=depth5, ws=ws5), ksteps, 1)
         if rank == 0:
             alg5 = n5 * W * H * 4
             configs["C5"] = {"workload": f"{P5} poses FIXED, UV sphere of {tris5.shape[0]} triangles, 640x480 int32 depth kept on the device, "

@@ -149,6 +149,53 @@ inline std::vector<std::vector<uint8_t>> raw2mask_uint8_cuda(device_vector_holde
     return out;
 }
 
+// raw2depth_mask_cuda (renderer.cu:409-439): upstream returns, per pose, a pair of cv::Mat {CV_16U depth, CV_8U mask};
+// without OpenCV the pair is this struct.  depth = uint16_t(raw) (truncation, renderer.cu:405), mask = raw > 0 ? 255 : 0.
+struct DepthMask {
+    std::vector<uint16_t> depth;
+    std::vector<uint8_t> mask;
+};
+inline std::vector<DepthMask> raw2depth_mask_cuda(device_vector_holder<int>& raw, size_t width, size_t height, size_t pose_size) {
+    if (raw.size() != width * height * pose_size) throw std::invalid_argument("raw2depth_mask_cuda: size mismatch");
+    device_vector_holder<uint16_t> d(raw.size());
+    device_vector_holder<uint8_t> m(raw.size());
+    check(pr_raw2depth_mask(raw.data(), raw.size(), d.data(), m.data(), nullptr), "pr_raw2depth_mask");
+    const std::vector<uint16_t> dall = d.download();
+    const std::vector<uint8_t> mall = m.download();
+    std::vector<DepthMask> out(pose_size);
+    const size_t step = width * height;
+    for (size_t i = 0; i < pose_size; i++) {
+        out[i].depth.assign(dall.begin() + i * step, dall.begin() + (i + 1) * step);
+        out[i].mask.assign(mall.begin() + i * step, mall.begin() + (i + 1) * step);
+    }
+    return out;
+}
+
+// The same two images straight from the rasteriser (pr_render_outputs_batch): the tile write-out stores uint16 depth and
+// the mask itself, the int32 batch is never materialised.  What PoseRenderer::render_* use.
+inline std::vector<DepthMask> render_depth_mask_cuda(device_vector_holder<Model::Triangle>& tris, const std::vector<Model::mat4x4>& poses,
+                                                     size_t width, size_t height, const Model::mat4x4& proj_mat,
+                                                     bool want_depth = true, bool want_mask = true) {
+    const size_t n = poses.size() * width * height;
+    device_vector_holder<uint16_t> d;
+    device_vector_holder<uint8_t> m;
+    if (want_depth) d.__malloc(n);
+    if (want_mask) m.__malloc(n);
+    const size_t ws_bytes = pr_render_workspace_bytes(poses.size(), tris.size(), width, height);
+    device_vector_holder<unsigned char> ws(ws_bytes);
+    const pr_roi none = {0, 0, 0, 0};
+    check(pr_render_outputs_batch(reinterpret_cast<const float*>(tris.data()), tris.size(), reinterpret_cast<const float*>(poses.data()), 0,
+                                  poses.size(), width, height, reinterpret_cast<const float*>(&proj_mat), none, nullptr,
+                                  want_depth ? d.data() : nullptr, want_mask ? m.data() : nullptr, ws.data(), ws_bytes, nullptr),
+          "pr_render_outputs_batch");
+    check(pr_stream_synchronize(nullptr), "sync");
+    std::vector<DepthMask> out(poses.size());
+    const size_t step = width * height;
+    if (want_depth) { const std::vector<uint16_t> all = d.download(); for (size_t i = 0; i < out.size(); i++) out[i].depth.assign(all.begin() + i * step, all.begin() + (i + 1) * step); }
+    if (want_mask) { const std::vector<uint8_t> all = m.download(); for (size_t i = 0; i < out.size(); i++) out[i].mask.assign(all.begin() + i * step, all.begin() + (i + 1) * step); }
+    return out;
+}
+
 // the dispatchers of renderer.h:230-248 (CUDA_ON branch)
 template <typename... Params> Int_holder render(Params&&... params) { return render_cuda_keep_in_gpu(std::forward<Params>(params)...); }
 template <typename... Params> std::vector<int32_t> render_host(Params&&... params) { return render_cuda(std::forward<Params>(params)...); }

@@ -18,16 +18,29 @@ public:
         std::memcpy(K, K_, 36); width = width_; height = height_;
         proj_mat = cuda_renderer::compute_proj(K, width, height);
     }
-    // init_poses: row-major 4x4 each
+    // init_poses: row-major 4x4 each.  pose_renderer.cpp:25-63: render at width/ds x height/ds with the FULL-resolution
+    // projection matrix, then raw2depth_uint16 / raw2mask_uint8 / raw2depth_mask.  Here the rasteriser writes the
+    // uint16 depth and the mask itself (pr_render_outputs_batch); the int32 batch never exists.
     std::vector<std::vector<uint16_t>> render_depth(const std::vector<cuda_renderer::Model::mat4x4>& init_poses, float down_sample = 1) {
-        const int w = int(width / down_sample), h = int(height / down_sample);
-        auto raw = cuda_renderer::render(tris, init_poses, (size_t)w, (size_t)h, proj_mat);
-        return cuda_renderer::raw2depth_uint16_cuda(raw, w, h, init_poses.size());
+        auto dm = render_what(init_poses, down_sample, true, false);
+        std::vector<std::vector<uint16_t>> out(dm.size());
+        for (size_t i = 0; i < dm.size(); i++) out[i] = std::move(dm[i].depth);
+        return out;
     }
     std::vector<std::vector<uint8_t>> render_mask(const std::vector<cuda_renderer::Model::mat4x4>& init_poses, float down_sample = 1) {
+        auto dm = render_what(init_poses, down_sample, false, true);
+        std::vector<std::vector<uint8_t>> out(dm.size());
+        for (size_t i = 0; i < dm.size(); i++) out[i] = std::move(dm[i].mask);
+        return out;
+    }
+    // pose -> {uint16 depth, uint8 mask} (upstream: std::vector<std::vector<cv::Mat>>, pose_renderer.cpp:56-63)
+    std::vector<cuda_renderer::DepthMask> render_depth_mask(const std::vector<cuda_renderer::Model::mat4x4>& init_poses, float down_sample = 1) {
+        return render_what(init_poses, down_sample, true, true);
+    }
+    std::vector<cuda_renderer::DepthMask> render_what(const std::vector<cuda_renderer::Model::mat4x4>& init_poses, float down_sample,
+                                                      bool want_depth, bool want_mask) {
         const int w = int(width / down_sample), h = int(height / down_sample);
-        auto raw = cuda_renderer::render(tris, init_poses, (size_t)w, (size_t)h, proj_mat);
-        return cuda_renderer::raw2mask_uint8_cuda(raw, w, h, init_poses.size());
+        return cuda_renderer::render_depth_mask_cuda(tris, init_poses, (size_t)w, (size_t)h, proj_mat, want_depth, want_mask);
     }
 };
 

@@ -161,6 +161,16 @@ int pr_render_cloud_batch(const float* verts_dev, size_t n_verts, const int32_t*
                           const pr_mesh_clusters* clusters /* nullable; faces must then be pr_mesh_cluster's order */,
                           void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
 
+/* PoseRenderer's outputs (pose_renderer.cpp:38-63: raw2depth_uint16 / raw2mask_uint8 / raw2depth_mask after render)   */
+/* folded into the rasteriser's tile write-out: out_depth16 = uint16_t(depth) (truncation, renderer.cu:405), out_mask =   */
+/* depth > 0 ? 255 : 0 (:406), n_poses * W' * H' each.  Any of the three outputs may be NULL (at least one is needed);     */
+/* with out_depth_dev == NULL the int32 batch is never written.  Needs the tile path's workspace                          */
+/* (pr_render_workspace_bytes).  Otherwise as pr_render_batch.                                                            */
+int pr_render_outputs_batch(const float* tris_dev, size_t n_tris, const float* poses, int poses_on_device, size_t n_poses,
+                            size_t width, size_t height, const float proj[16], pr_roi roi, int32_t* out_depth_dev,
+                            uint16_t* out_depth16_dev, uint8_t* out_mask_dev,
+                            void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
+
 /* Parity entry point: the rasteriser divides with a refined reciprocal + residual correction instead of the       */
 /* div.rn.f32 call (raster.cu, "IEEE division without the library call").  Compares n pseudo-random quotients      */
 /* over the operand ranges the kernel guarantees with div.rn.f32; *mismatches_dev (uint64) must end up 0.          */

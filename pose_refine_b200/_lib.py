@@ -44,6 +44,7 @@ PROTOTYPES = {
     "pr_compute_proj": (_i, [_vp, _i, _i, _f, _f, _vp]),
     "pr_render_workspace_bytes": (_sz, [_sz, _sz, _sz, _sz]),
     "pr_render_batch": (_i, [_vp, _sz, _vp, _i, _sz, _sz, _sz, _vp, Roi, _vp, _vp, _sz, _vp]),
+    "pr_render_outputs_batch": (_i, [_vp, _sz, _vp, _i, _sz, _sz, _sz, _vp, Roi, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pr_mesh_index": (_i, [_vp, _sz, _vp, _vp, C.POINTER(_sz)]),
     "pr_render_indexed_workspace_bytes": (_sz, [_sz, _sz, _sz, _sz, _sz]),
     "pr_render_indexed_batch": (_i, [_vp, _sz, _vp, _sz, _vp, _i, _sz, _sz, _sz, _vp, Roi, _vp, _vp, _sz, _vp]),

@@ -139,6 +139,56 @@ def render_cuda_keep_in_gpu(tris, poses, width, height, proj_mat, roi=(0, 0, 0, 
     return out
 
 
+def render_depth_mask_cuda(tris, poses, width, height, proj_mat, want_depth=True, want_mask=True, want_raw=False, roi=(0, 0, 0, 0)):
+    """The rasteriser with PoseRenderer's outputs folded into its write-out (pr_render_outputs_batch):
+    -> (uint16 depth [P,H',W'] or None, uint8 mask [P,H',W'] or None, int32 raw [P,H',W'] or None), cuda tensors."""
+    _require_device()
+    tris = _dev(tris, torch.float32).reshape(-1, 9)
+    proj = _f32c(proj_mat).reshape(16)
+    roi_c = _lib.Roi(*[int(v) for v in roi])
+    rw, rh = (roi_c.width, roi_c.height) if roi_c.width > 0 and roi_c.height > 0 else (width, height)
+    poses_t = _dev(poses, torch.float32).reshape(-1, 16)
+    P = poses_t.shape[0]
+    d16 = torch.empty((P, rh, rw), dtype=torch.uint16, device="cuda") if want_depth else None
+    m8 = torch.empty((P, rh, rw), dtype=torch.uint8, device="cuda") if want_mask else None
+    raw = torch.empty((P, rh, rw), dtype=torch.int32, device="cuda") if want_raw else None
+    ws_bytes = lib().pr_render_workspace_bytes(P, tris.shape[0], width, height)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    check(lib().pr_render_outputs_batch(tris.data_ptr(), tris.shape[0], poses_t.data_ptr(), 1, P, width, height, proj.ctypes.data, roi_c,
+                                        raw.data_ptr() if want_raw else None, d16.data_ptr() if want_depth else None,
+                                        m8.data_ptr() if want_mask else None, ws.data_ptr(), ws_bytes, _stream()), "pr_render_outputs_batch")
+    return d16, m8, raw
+
+
+class PoseRenderer:
+    """PoseRenderer (pose_renderer.h:9-32, pose_renderer.cpp): model uploaded once, batches of poses rendered to uint16
+    depth / uint8 mask; down_sample renders at width/ds x height/ds with the FULL-resolution projection
+    (pose_renderer.cpp:25-36)."""
+
+    def __init__(self, tris_or_path):
+        _require_device()
+        tris = load_ply(tris_or_path) if isinstance(tris_or_path, str) else _f32c(tris_or_path).reshape(-1, 9)
+        self.tris = torch.as_tensor(tris).cuda()
+
+    def set_K_width_height(self, K, width, height):
+        self.K, self.width, self.height = _f32c(K).reshape(3, 3), int(width), int(height)
+        self.proj_mat = compute_proj(self.K, self.width, self.height)
+
+    def _render(self, init_poses, down_sample, want_depth, want_mask):
+        w, h = int(self.width / down_sample), int(self.height / down_sample)
+        return render_depth_mask_cuda(self.tris, init_poses, w, h, self.proj_mat, want_depth, want_mask)
+
+    def render_depth(self, init_poses, down_sample=1):
+        return self._render(init_poses, down_sample, True, False)[0]
+
+    def render_mask(self, init_poses, down_sample=1):
+        return self._render(init_poses, down_sample, False, True)[1]
+
+    def render_depth_mask(self, init_poses, down_sample=1):
+        d, m, _ = self._render(init_poses, down_sample, True, True)
+        return d, m
+
+
 def mesh_index(tris):
     """Deduplicate a triangle soup [T,9] -> (vertices [V,3] float32, faces [T,3] int32) (pr_mesh_index, host)."""
     tris = _f32c(tris).reshape(-1, 9)

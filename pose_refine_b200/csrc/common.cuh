@@ -27,7 +27,12 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
 
 inline cudaStream_t as_stream(pr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
-constexpr int kNumSMs = 148;  // B200
+// SMs of the current device (grid sizing of the grid-stride kernels); 148 on a B200
+inline int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    return n;
+}
 
 // IEEE single ops that the compiler may never contract into FMA: the rasteriser and the cloud /
 // scene-preparation kernels use them so their results equal the reference's x86 CPU build

@@ -56,5 +56,21 @@ int main(int argc, char** argv) {
     for (const auto& b : batch)
         for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) worst = std::fmax(worst, std::fabs(b.transformation_[i][j] - result.transformation_[i][j]));
     std::printf("batch refiner: max |T_batch - T_single| = %.3g, fitness %.6f\n", worst, batch[0].fitness_);
+    // PoseRenderer (pose_renderer.h:9-32): both fixture poses, full size and down_sample = 2 (width/2 x height/2 with the
+    // full-resolution projection, pose_renderer.cpp:25-36); printed sums are checked against the oracle by the test
+    PoseRenderer pr(argv[1]);
+    pr.set_K_width_height(K, width, height);
+    for (float ds : {1.0f, 2.0f}) {
+        auto dm = pr.render_depth_mask(mat4_v, ds);
+        auto only_depth = pr.render_depth(mat4_v, ds);
+        auto only_mask = pr.render_mask(mat4_v, ds);
+        for (size_t i = 0; i < dm.size(); i++) {
+            unsigned long long sum = 0, cnt = 0;
+            for (uint16_t v : dm[i].depth) sum += v;
+            for (uint8_t v : dm[i].mask) cnt += (v == 255);
+            const bool same = only_depth[i] == dm[i].depth && only_mask[i] == dm[i].mask;
+            std::printf("pose_renderer ds %.0f pose %zu size %zu depth_sum %llu mask_count %llu consistent %d\n", ds, i, dm[i].depth.size(), sum, cnt, (int)same);
+        }
+    }
     return (result.fitness_ > 0.9f && worst < 5e-4f) ? 0 : 1;
 }

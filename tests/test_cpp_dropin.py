@@ -10,14 +10,15 @@ import pytest
 from conftest import ROOT
 
 SRC = os.path.join(ROOT, "tests", "cpp", "dropin_demo.cpp")
+SRC_MULTI = os.path.join(ROOT, "tests", "cpp", "multi_gpu_demo.cpp")
 
 
-def _build(tmp_path):
+def _build(tmp_path, src=SRC, name="dropin_demo"):
     from pose_refine_b200 import build
     build()
-    exe = str(tmp_path / "dropin_demo")
+    exe = str(tmp_path / name)
     libdir = os.path.join(ROOT, "pose_refine_b200")
-    cmd = ["/usr/bin/g++", "-std=c++14", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), SRC, "-L", libdir,
+    cmd = ["/usr/bin/g++", "-std=c++14", "-O2", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"), src, "-L", libdir,
            "-lpose_refine_b200", f"-Wl,-rpath,{libdir}", "-o", exe]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
@@ -38,6 +39,21 @@ def _write_ascii_ply(path):
 
 def test_dropin_headers_compile_and_link(tmp_path):
     assert os.path.exists(_build(tmp_path))
+    assert os.path.exists(_build(tmp_path, SRC_MULTI, "multi_gpu_demo"))
+
+
+@pytest.mark.gpu
+def test_multi_gpu_demo_shards_add_up(tmp_path):
+    """tests/cpp/multi_gpu_demo.cpp: one host thread per GPU through pr_comm_* / pr_broadcast_scene / pr_gather_results;
+    the gathered shard results of every rank equal the single-GPU batch bit for bit.  On a one-GPU box this runs the
+    one-rank path (no NCCL); `gpurun --gpus 2 -- pytest -k multi_gpu` runs it with two ranks."""
+    exe = _build(tmp_path, SRC_MULTI, "multi_gpu_demo")
+    ply = str(tmp_path / "obj_06.ply")
+    _write_ascii_ply(ply)
+    res = subprocess.run([exe, ply], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "mismatching_ranks 0" in res.stdout, res.stdout
+    print(res.stdout.strip())
 
 
 @pytest.mark.gpu
@@ -57,3 +73,18 @@ def test_dropin_demo_matches_oracle(tmp_path, golden):
         # default criteria stop on float-order-dependent tests: +-1 pass moves T by ~1.5e-4
         assert np.abs(T.reshape(-1) - want[:16]).max() < 5e-4, (T, want[:16].reshape(4, 4))
         assert abs(float(head[3]) - want[17]) < 5e-3
+        # PoseRenderer::render_depth / render_mask / render_depth_mask, down_sample 1 and 2, against the oracle's render at
+        # W/ds x H/ds with the full-resolution projection (pose_renderer.cpp:25-36) + the raw2* conversions
+        from oracle import binding
+        from pose_refine_b200 import workloads as wl
+        port = binding.load("port")
+        mesh = wl.load_mesh_npz(os.path.join(ROOT, "tests", "golden", "obj_06_mesh.npz"))
+        rows = [ln.split() for ln in lines if ln.startswith("pose_renderer")]
+        assert len(rows) == 4
+        for row in rows:
+            ds, i = int(float(row[2])), int(row[4])
+            w, h = 640 // ds, 480 // ds
+            raw = port.render(mesh, arrays["poses"][i: i + 1], w, h, arrays["proj"])[0]
+            d16, m8 = port.raw2depth_mask(raw)
+            assert int(row[6]) == w * h and int(row[8]) == int(d16.astype(np.int64).sum()) and int(row[10]) == int((m8 == 255).sum())
+            assert int(row[12]) == 1

@@ -238,6 +238,41 @@ def test_raw2depth_mask(api, port, fixture_scene, torch_mod):
 
 # ---------------------------------------------------------------------------------------------
 # depth2cloud
+def test_pose_renderer_outputs_folded_into_the_rasteriser(api, port, mesh, golden, torch_mod):
+    """pr_render_outputs_batch / PoseRenderer (pose_renderer.cpp:25-63): uint16 depth and mask written by the tile
+    write-out equal raw2depth_uint16 / raw2mask_uint8 of the oracle's render, bit for bit -- full size, down_sample 2
+    (half-size image with the FULL-resolution projection), an odd size (scalar stores) and a ROI; the uint16 truncation
+    (renderer.cu:405) is exercised by a mesh scaled so that depths exceed 65535."""
+    arrays, _ = golden
+    K, proj, poses = arrays["K"], arrays["proj"], arrays["poses"]
+    pr = api.PoseRenderer(mesh)
+    pr.set_K_width_height(K, 640, 480)
+    for ds in (1, 2):
+        w, h = 640 // ds, 480 // ds
+        raw = port.render(mesh, poses, w, h, proj)
+        want_d, want_m = port.raw2depth_mask(raw)
+        d, m = pr.render_depth_mask(poses, ds)
+        assert np.array_equal(d.cpu().numpy(), want_d) and np.array_equal(m.cpu().numpy(), want_m)
+        assert np.array_equal(pr.render_depth(poses, ds).cpu().numpy(), want_d)
+        assert np.array_equal(pr.render_mask(poses, ds).cpu().numpy(), want_m)
+    # odd size + all three outputs at once; ROI
+    for (w, h, roi) in ((333, 251, (0, 0, 0, 0)), (640, 480, wl.ROI_FIXTURE)):
+        pj = port.compute_proj(K, w, h)
+        raw = port.render(mesh, poses, w, h, pj, roi)
+        want_d, want_m = port.raw2depth_mask(raw)
+        d, m, r = api.render_depth_mask_cuda(mesh, poses, w, h, pj, want_raw=True, roi=roi)
+        assert np.array_equal(r.cpu().numpy(), raw) and np.array_equal(d.cpu().numpy(), want_d) and np.array_equal(m.cpu().numpy(), want_m)
+    # depths beyond 16 bits: the object 300x larger and farther away
+    big = (mesh * np.float32(300)).astype(np.float32)
+    far = poses.copy(); far[:, :3, 3] *= np.float32(300)
+    pj = port.compute_proj(K, 640, 480, 10.0, 1e7)
+    raw = port.render(big, far, 640, 480, pj)
+    assert raw.max() > 65535
+    want_d, want_m = port.raw2depth_mask(raw)
+    d, m, _ = api.render_depth_mask_cuda(big, far, 640, 480, pj)
+    assert np.array_equal(d.cpu().numpy(), want_d) and np.array_equal(m.cpu().numpy(), want_m)
+
+
 def test_depth2cloud_bit_exact(api, port, mesh, golden, torch_mod):
     arrays, scal = golden
     K = arrays["K"]
