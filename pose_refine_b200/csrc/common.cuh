@@ -61,4 +61,10 @@ int cloud_from_tiles(const int32_t* depth_dev, size_t n_images, uint32_t width, 
                      uint32_t* counts_dev, uint32_t* offsets_dev, uint32_t* overflow_dev, size_t capacity_points,
                      uint32_t align_points, float* out_pts_dev, cudaStream_t stream);
 
+// icp.cu: pr_icp_projective_batch_packed with the caller's estimate of the average cloud size (steers the cluster size)
+int icp_projective_packed(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_dev, size_t n_hyp,
+                          size_t capacity_points, const pr_scene_projective* scene, const void* packed_dev,
+                          pr_icp_criteria criteria, pr_registration_result* results_dev, int flags,
+                          void* workspace_dev, size_t workspace_bytes, pr_stream_t stream, size_t pts_per_hyp);
+
 }  // namespace prb

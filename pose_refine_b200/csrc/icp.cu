@@ -917,18 +917,21 @@ inline int device_info(DeviceInfo& out) {
 #ifndef PR_HYP_CLUSTER_MIN
 #define PR_HYP_CLUSTER_MIN 2
 #endif
-inline int pick_cluster(size_t n_hyp, int sms, int min_blocks) {
+constexpr size_t kL2BudgetBytes = 80u << 20;    // what the clouds of the hypotheses in flight may occupy of the 126 MB L2
+inline int pick_cluster(size_t n_hyp, int sms, int min_blocks, size_t pts_per_hyp) {
 #ifdef PR_DEBUG       // experiment builds only (scripts/build_variants.py)
     if (const char* e = getenv("PR_HYP_CLUSTER")) { const int c = atoi(e); if (c == 1 || c == 2 || c == 4 || c == 8) return c; }
 #endif
     if (PR_HYP_CLUSTER > 0) return PR_HYP_CLUSTER;
-    // the smallest cluster that still fills the machine: n_hyp * C >= resident CTAs (a small batch spreads each
-    // hypothesis over more SMs), and never below 2 -- measured on 512 hypotheses x 22k points (592 resident CTAs):
-    // C = 1 1.60 ms, C = 2 1.45 ms, C = 4 1.54 ms: two CTAs per hypothesis halve what the claim counter hands out at the
-    // end of the launch, and the pairwise exchange is one st.async per lane
+    // (1) the smallest cluster that still fills the machine: n_hyp * C >= resident CTAs (a small batch spreads each
+    //     hypothesis over more SMs), never below 2 -- measured on 512 hypotheses x 22k points (592 resident CTAs):
+    //     C = 1 1.65 ms, C = 2 1.42 ms, C = 4 1.54 ms, C = 8 1.93 ms; 64 hypotheses: C = 2 0.50 ms, 4 0.36 ms, 8 0.29 ms.
+    // (2) the clouds of the hypotheses in flight (resident CTAs / C of them) must stay in L2, or every pass streams
+    //     from HBM again: 512 hypotheses x 88k points (1280x720): C = 2 5.86 ms, C = 4 5.77 ms, C = 8 5.30 ms.
     const size_t slots = (size_t)sms * (size_t)min_blocks;
     int c = PR_HYP_CLUSTER_MIN;
     while (c < kMaxCluster && n_hyp * (size_t)c < slots) c <<= 1;
+    while (c < kMaxCluster && (slots / (size_t)c) * pts_per_hyp * 12 > kL2BudgetBytes) c <<= 1;
     return c;
 }
 
@@ -937,14 +940,13 @@ inline int pick_cluster_nn(size_t n_hyp, int sms, int min_blocks) {
 #ifdef PR_DEBUG
     if (const char* e = getenv("PR_NN_CLUSTER")) { const int c = atoi(e); if (c == 1 || c == 2 || c == 4 || c == 8) return c; }
 #endif
-    return pick_cluster(n_hyp, sms, min_blocks);
+    return pick_cluster(n_hyp, sms, min_blocks, 0);
 }
 
 template <class SceneT>
 int launch_hyp(const float* pts_dev, size_t capacity_points, const uint32_t* offsets_dev, const uint32_t* counts_dev, size_t n_hyp,
                const IcpWs& ws, const SceneT& scene, pr_icp_criteria crit, pr_registration_result* results_dev, float* out32,
-               size_t extra_smem_unused, cudaStream_t stream) {
-    (void)extra_smem_unused;
+               size_t pts_per_hyp, cudaStream_t stream) {
     using Tr = HypTraits<SceneT>;
     DeviceInfo di;
     int rc = device_info(di);
@@ -952,7 +954,7 @@ int launch_hyp(const float* pts_dev, size_t capacity_points, const uint32_t* off
     const size_t smem = hyp_smem<Tr::kWarps>(Tr::kExtraSmem);
     auto kernel = icp_hyp_kernel<SceneT>;
     PR_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int C = Tr::kProjective ? pick_cluster(n_hyp, di.sms, Tr::kMinBlocks) : pick_cluster_nn(n_hyp, di.sms, Tr::kMinBlocks);
+    const int C = Tr::kProjective ? pick_cluster(n_hyp, di.sms, Tr::kMinBlocks, pts_per_hyp) : pick_cluster_nn(n_hyp, di.sms, Tr::kMinBlocks);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cudaLaunchAttribute attr[1];
@@ -995,7 +997,8 @@ int launch_hyp(const float* pts_dev, size_t capacity_points, const uint32_t* off
 template <class SceneT, class PScene>
 int run_icp(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_dev, size_t n_hyp, size_t capacity_points,
             const SceneT& scene, const PScene& pscene, pr_icp_criteria crit, pr_registration_result* results_dev, int flags,
-            const IcpWs& ws, cudaStream_t stream) {
+            const IcpWs& ws, cudaStream_t stream, size_t pts_per_hyp = 0) {
+    if (pts_per_hyp == 0) pts_per_hyp = n_hyp ? capacity_points / n_hyp : 0;      // the caller's buffer bounds the clouds
     if (flags & PR_ICP_REFERENCE_ARITHMETIC) {
         DeviceInfo di;
         int rc = device_info(di);
@@ -1017,7 +1020,7 @@ int run_icp(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_
         PR_LAUNCH_CHECK();
         return PR_OK;
     }
-    int rc = launch_hyp(pts_dev, capacity_points, offsets_dev, counts_dev, n_hyp, ws, pscene, crit, results_dev, nullptr, 0, stream);
+    int rc = launch_hyp(pts_dev, capacity_points, offsets_dev, counts_dev, n_hyp, ws, pscene, crit, results_dev, nullptr, pts_per_hyp, stream);
     if (rc != PR_OK) return rc;
     if (flags & PR_ICP_UPDATE_POINTS) {
         icp_apply_kernel<<<(unsigned)(n_hyp * kApplySlices), 256, 0, stream>>>(pts_dev, offsets_dev, counts_dev, (unsigned)n_hyp, ws.final_T);
@@ -1134,10 +1137,13 @@ int pr_scene_projective_pack(const pr_scene_projective* scene, void* packed_dev,
     return PR_OK;
 }
 
-int pr_icp_projective_batch_packed(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_dev, size_t n_hyp,
-                                   size_t capacity_points, const pr_scene_projective* scene, const void* packed_dev,
-                                   pr_icp_criteria criteria, pr_registration_result* results_dev, int flags,
-                                   void* workspace_dev, size_t workspace_bytes, pr_stream_t stream_) {
+}  // extern "C"
+
+// pts_per_hyp: the caller's estimate of the average cloud size (0: capacity_points / n_hyp); only steers the cluster size
+int prb::icp_projective_packed(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_dev, size_t n_hyp,
+                               size_t capacity_points, const pr_scene_projective* scene, const void* packed_dev,
+                               pr_icp_criteria criteria, pr_registration_result* results_dev, int flags,
+                               void* workspace_dev, size_t workspace_bytes, pr_stream_t stream_, size_t pts_per_hyp) {
     ProjScene s;
     int rc = make_proj_scene(scene, s);
     if (rc != PR_OK) return rc;
@@ -1155,7 +1161,17 @@ int pr_icp_projective_batch_packed(float* pts_dev, const uint32_t* offsets_dev, 
         count_launch();
     }
     const PackedScene ps = make_packed_scene(s, own_pack ? ws.packed : (const float4*)packed_dev);
-    return run_icp(pts_dev, offsets_dev, counts_dev, n_hyp, capacity_points, s, ps, criteria, results_dev, flags, ws, stream);
+    return run_icp(pts_dev, offsets_dev, counts_dev, n_hyp, capacity_points, s, ps, criteria, results_dev, flags, ws, stream, pts_per_hyp);
+}
+
+extern "C" {
+
+int pr_icp_projective_batch_packed(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_dev, size_t n_hyp,
+                                   size_t capacity_points, const pr_scene_projective* scene, const void* packed_dev,
+                                   pr_icp_criteria criteria, pr_registration_result* results_dev, int flags,
+                                   void* workspace_dev, size_t workspace_bytes, pr_stream_t stream) {
+    return prb::icp_projective_packed(pts_dev, offsets_dev, counts_dev, n_hyp, capacity_points, scene, packed_dev, criteria, results_dev,
+                                      flags, workspace_dev, workspace_bytes, stream, 0);
 }
 
 int pr_icp_projective_batch(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_dev, size_t n_hyp,

@@ -43,7 +43,8 @@ struct pr_refiner {
     size_t scene_ws_bytes = 0;
     pr_scene_projective sp;
     pr_scene_nn sn;
-    uint32_t* h_overflow = nullptr;   // pinned
+    uint32_t pending_hyp = 0;
+    uint32_t* h_overflow = nullptr;   // pinned: [0] overflow flag, [1] total points of the last batch (padded)
 };
 
 namespace {
@@ -70,9 +71,20 @@ int run_device(pr_refiner* r, const float* poses_dev, size_t n_hyp, pr_icp_crite
                                    r->d_depth, r->d_pts, r->capacity_points, 4, r->d_counts, r->d_offsets, r->d_overflow,
                                    &r->clusters, r->ws_render, r->ws_render_bytes, s);
     if (rc != PR_OK) return rc;
-    if (r->scene_kind == 0)
-        return pr_icp_projective_batch_packed(r->d_pts, r->d_offsets, r->d_counts, n_hyp, r->capacity_points, &r->sp, r->d_scene_packed,
-                                              crit, results_dev, 0, r->ws_icp, r->ws_icp_bytes, s);
+    if (r->scene_kind == 0) {
+        // average cloud size, for the cluster size of the ICP launch: what the previous batch had (its total is copied to
+        // pinned memory behind every run, asynchronously: a stale or missing value only costs a less suitable cluster
+        // size); the first batch assumes the object covers 1/14 of the image
+        volatile uint32_t* hint = r->h_overflow;
+        const size_t est = (hint[1] != 0 && r->pending_hyp != 0) ? (size_t)hint[1] / r->pending_hyp : ((size_t)r->W * r->H) / 14;
+        rc = prb::icp_projective_packed(r->d_pts, r->d_offsets, r->d_counts, n_hyp, r->capacity_points, &r->sp, r->d_scene_packed,
+                                        crit, results_dev, 0, r->ws_icp, r->ws_icp_bytes, s, est ? est : 1);
+        if (rc != PR_OK) return rc;
+        if (cudaMemcpyAsync(r->h_overflow + 1, r->d_offsets + n_hyp, 4, cudaMemcpyDeviceToHost, stream) == cudaSuccess)
+            r->pending_hyp = (uint32_t)n_hyp;      // batch size that total belongs to (a total that has not landed yet pairs an
+                                                   // older total with this size for one call: a heuristic, not a contract)
+        return PR_OK;
+    }
     return pr_icp_nn_batch(r->d_pts, r->d_offsets, r->d_counts, n_hyp, r->capacity_points, &r->sn, crit, results_dev, 0,
                            r->ws_icp, r->ws_icp_bytes, s);
 }
@@ -175,6 +187,7 @@ int pr_refiner_create(pr_refiner** out, const float* tris_host, size_t n_tris, u
     alloc(&r->ws_cloud, r->ws_cloud_bytes);
     alloc(&r->ws_icp, r->ws_icp_bytes);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&r->h_overflow, 256);
+    if (e == cudaSuccess) memset(r->h_overflow, 0, 256);
     if (e == cudaSuccess) e = cudaMemcpy(r->d_tris, tris_host, n_tris * 36, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(r->d_verts, verts.data(), r->n_verts * 12, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(r->d_faces, faces.data(), n_tris * 12, cudaMemcpyHostToDevice);

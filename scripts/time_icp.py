@@ -13,23 +13,25 @@ P = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 clusters = [int(c) for c in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
 mesh = wl.load_mesh_npz(os.path.join(ROOT, "tests", "golden", "obj_06_mesh.npz"))
-K = wl.LINEMOD_K
-proj = api.compute_proj(K, 640, 480)
+BIG = os.environ.get("RES") == "720"          # C4: 1280x720, ~88k points per hypothesis
+W_, H_ = (1280, 720) if BIG else (640, 480)
+K = wl.k_1280x720() if BIG else wl.LINEMOD_K
+proj = api.compute_proj(K, W_, H_)
 _, scene_pose = wl.fixture_poses()
-scene_depth = api.render_cuda(mesh, scene_pose[None], 640, 480, proj)[0]
+scene_depth = api.render_cuda(mesh, scene_pose[None], W_, H_, proj)[0]
 verts, faces = api.mesh_index(mesh)
 faces, off, cv = api.mesh_cluster(verts, faces)
-depth, pts, offsets, counts = api.render_cloud_batch(verts, faces, wl.hypotheses(P, seed=1234), 640, 480, proj, K,
-                                                     capacity_points=P * 40000, clusters=(off, cv))
+depth, pts, offsets, counts = api.render_cloud_batch(verts, faces, wl.hypotheses(P, seed=4321 if BIG else 1234), W_, H_, proj, K,
+                                                     capacity_points=P * (140000 if BIG else 40000), clusters=(off, cv))
 del depth
-scene = api.SceneProjective().init_cuda(scene_depth, K)
+scene = api.SceneProjective().init_cuda(scene_depth, K, W_, H_)
 L = _lib.lib()
-cap = pts.shape[0]
-ws_bytes = L.pr_icp_workspace_bytes(P, cap, 640 * 480)
+cap = int(offsets[P].item())
+ws_bytes = L.pr_icp_workspace_bytes(P, cap, W_ * H_)
 ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
 res = torch.empty((P, 18), dtype=torch.float32, device="cuda")
 sc = scene.c()
-packed = torch.empty(L.pr_scene_projective_packed_bytes(640, 480), dtype=torch.uint8, device="cuda")
+packed = torch.empty(L.pr_scene_projective_packed_bytes(W_, H_), dtype=torch.uint8, device="cuda")
 stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 assert L.pr_scene_projective_pack(C.byref(sc), packed.data_ptr(), stream) == 0
 crit = _lib.Criteria(0.0, 0.0, 30)
@@ -52,7 +54,7 @@ for c in clusters:
     r = res.cpu().numpy()
     if ref is None: ref = r.copy()
     good = ref[:, 17] > 0.9
-    alg = (12 * n_pts + 640 * 480 * 24 + 72 * P) * 31
+    alg = (12 * n_pts + W_ * H_ * 24 + 72 * P) * 31
     print(json.dumps({"lib": os.path.basename(os.environ.get("PR_LIB", "default")), "cluster": c, "icp_ms": round(ms, 4), "min_ms": round(min(ts), 4),
                       "GBs": round(alg / (ms * 1e-3) / 1e9, 1), "frac": round(alg / (ms * 1e-3) / 1e9 / 6553.3, 4),
                       "max_dev_vs_first": float(np.abs(r[good, :16] - ref[good, :16]).max()), "n_converged": int(good.sum())}), flush=True)
