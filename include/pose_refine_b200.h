@@ -338,6 +338,11 @@ int pr_refiner_buffers(pr_refiner* r, const int32_t** depth_dev, const float** p
 /* and the device copy of the results of the last pr_refiner_run (host variant).  Any pointer may be NULL.               */
 int pr_refiner_scene_buffers(pr_refiner* r, const float** scene_pcd_dev, const float** scene_normal_dev,
                              const pr_registration_result** results_dev);
+/* Device time of the two stages of the runs since the last call (at most the last 256), from CUDA events the refiner      */
+/* records on the caller's stream around the fused render -> cloud call and around the ICP call of every run: the mean per  */
+/* run, in milliseconds, and how many runs it covers.  Synchronises with the last of them.  This is how bench.py measures   */
+/* the ICP kernel INSIDE its timed steps.                                                                                    */
+int pr_refiner_stage_ms(pr_refiner* r, float* render_cloud_ms, float* icp_ms, uint32_t* n_runs);
 /* kernel launches issued by this library since load (all entry points), for bench accounting.    */
 uint64_t pr_launch_count(void);
 

@@ -75,6 +75,7 @@ PROTOTYPES = {
     "pr_refiner_run_device": (_i, [_vp, _vp, _sz, Criteria, _vp, _vp]),
     "pr_refiner_buffers": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "pr_refiner_scene_buffers": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "pr_refiner_stage_ms": (_i, [_vp, C.POINTER(_f), C.POINTER(_f), C.POINTER(_u32)]),
     "pr_launch_count": (C.c_uint64, []),
     "pr_debug_div_check": (_i, [C.c_uint64, _u32, _vp, _vp]),
     "pr_scene_projective_packed_bytes": (_sz, [_u32, _u32]),

@@ -619,6 +619,13 @@ class PoseRefiner:
               "pr_refiner_run_device")
         return results_dev
 
+    def stage_ms(self):
+        """(mean render->cloud ms, mean ICP ms, number of runs) of the runs since the last call, from the CUDA events the
+        refiner records around its two stages."""
+        a, b, n = C.c_float(), C.c_float(), C.c_uint32()
+        check(lib().pr_refiner_stage_ms(self._h, C.byref(a), C.byref(b), C.byref(n)), "pr_refiner_stage_ms")
+        return a.value, b.value, n.value
+
     def scene_buffers(self):
         """Views of the prepared projective scene: (pcd [W*H,3], normal [W*H,3]) float32 on the device."""
         p, n = C.c_void_p(), C.c_void_p()

@@ -44,6 +44,10 @@ struct pr_refiner {
     pr_scene_projective sp;
     pr_scene_nn sn;
     uint32_t pending_hyp = 0;
+    // stage timing: three events per run (start, after render->cloud, after ICP), a ring of the last kTimedRuns runs
+    static constexpr int kTimedRuns = 256;
+    cudaEvent_t ev[kTimedRuns][3] = {};
+    unsigned ev_next = 0, ev_count = 0;
     uint32_t* h_overflow = nullptr;   // pinned: [0] overflow flag, [1] total points of the last batch (padded)
 };
 
@@ -66,11 +70,19 @@ int ensure(void** p, size_t bytes) {
 int run_device(pr_refiner* r, const float* poses_dev, size_t n_hyp, pr_icp_criteria crit,
                pr_registration_result* results_dev, cudaStream_t stream) {
     pr_stream_t s = reinterpret_cast<pr_stream_t>(stream);
+    cudaEvent_t* ev = r->ev[r->ev_next];
+    if (!ev[0]) for (int i = 0; i < 3; i++) PR_CUDA_TRY(cudaEventCreate(&ev[i]));
+    struct StageEnd {       // the closing event of a run is recorded on every way out
+        pr_refiner* r; cudaEvent_t e; cudaStream_t st;
+        ~StageEnd() { cudaEventRecord(e, st); r->ev_next = (r->ev_next + 1) % pr_refiner::kTimedRuns; if (r->ev_count < (unsigned)pr_refiner::kTimedRuns) r->ev_count++; }
+    } stage_end{r, ev[2], stream};
+    PR_CUDA_TRY(cudaEventRecord(ev[0], stream));
     // render + clouds in one pass over the depth batch (tile-ordered clouds; the reduction does not care about order)
     int rc = pr_render_cloud_batch(r->d_verts, r->n_verts, r->d_faces, r->n_tris, poses_dev, 1, n_hyp, r->W, r->H, r->proj, r->K,
                                    r->d_depth, r->d_pts, r->capacity_points, 4, r->d_counts, r->d_offsets, r->d_overflow,
                                    &r->clusters, r->ws_render, r->ws_render_bytes, s);
     if (rc != PR_OK) return rc;
+    PR_CUDA_TRY(cudaEventRecord(ev[1], stream));
     if (r->scene_kind == 0) {
         // average cloud size, for the cluster size of the ICP launch: what the previous batch had (its total is copied to
         // pinned memory behind every run, asynchronously: a stale or missing value only costs a less suitable cluster
@@ -206,6 +218,7 @@ void pr_refiner_destroy(pr_refiner* r) {
     cudaFree(r->d_tris); cudaFree(r->d_verts); cudaFree(r->d_faces); cudaFree(r->d_cl_off); cudaFree(r->d_cl_verts); cudaFree(r->d_poses); cudaFree(r->d_depth); cudaFree(r->d_pts);
     cudaFree(r->d_counts); cudaFree(r->d_offsets); cudaFree(r->d_overflow); cudaFree(r->d_results);
     cudaFree(r->ws_render); cudaFree(r->ws_cloud); cudaFree(r->ws_icp);
+    for (auto& e3 : r->ev) for (auto& e : e3) if (e) cudaEventDestroy(e);
     if (r->h_overflow) cudaFreeHost(r->h_overflow);
     delete r;
 }
@@ -310,6 +323,25 @@ int pr_refiner_buffers(pr_refiner* r, const int32_t** depth_dev, const float** p
     if (pts_dev) *pts_dev = r->d_pts;
     if (offsets_dev) *offsets_dev = r->d_offsets;
     if (counts_dev) *counts_dev = r->d_counts;
+    return PR_OK;
+}
+
+int pr_refiner_stage_ms(pr_refiner* r, float* render_cloud_ms, float* icp_ms, uint32_t* n_runs) {
+    if (!r) return PR_ERR_INVALID_ARGUMENT;
+    double a = 0.0, b = 0.0;
+    unsigned n = 0;
+    for (unsigned k = 0; k < r->ev_count; k++) {
+        cudaEvent_t* ev = r->ev[(r->ev_next + pr_refiner::kTimedRuns - 1 - k) % pr_refiner::kTimedRuns];
+        if (!ev[0]) continue;
+        PR_CUDA_TRY(cudaEventSynchronize(ev[2]));
+        float t0 = 0.f, t1 = 0.f;
+        if (cudaEventElapsedTime(&t0, ev[0], ev[1]) != cudaSuccess || cudaEventElapsedTime(&t1, ev[1], ev[2]) != cudaSuccess) { cudaGetLastError(); continue; }
+        a += t0; b += t1; n++;
+    }
+    if (render_cloud_ms) *render_cloud_ms = n ? (float)(a / n) : 0.f;
+    if (icp_ms) *icp_ms = n ? (float)(b / n) : 0.f;
+    if (n_runs) *n_runs = n;
+    r->ev_count = 0;
     return PR_OK;
 }
 
