@@ -562,16 +562,23 @@ __device__ __noinline__ float slow_slice(const PackedScene& s, const float* __re
     return warp_transpose_reduce(v);
 }
 
-// a warp's slice against the kd-tree: lane l takes points l, l + 32, ...  `cache` (nullable): one int per point of the
-// slice, the winner of the previous pass, which seeds this pass' search (nn_search_packed_t); pass 0 only writes it.
-__device__ __forceinline__ void compute_slice_nn(const PackedNnScene& s, const float* __restrict__ g, unsigned n, unsigned t_addr, AccT& acc,
-                                                 int* __restrict__ cache, bool use_cache) {
+// A warp's share of one hypothesis against the kd-tree: 32-point rows dealt round-robin to the G warps of the cluster (row
+// k goes to warp k mod G), not one contiguous slice per warp -- the cost of a walk varies over the object, neighbouring points
+// cost about the same, and with contiguous slices the warps of a pass finished far apart (a quarter of all stall samples at
+// the pass-end barrier; 107 -> 63 ms per C3 step together with the two-phase walk of nn_search_packed_t).  `cache`
+// (nullable): one int per point of the hypothesis, the winner of the previous pass, which seeds this pass' search; pass 0
+// only writes it.
+// (Tried: lanes as persistent workers -- a lane whose walk is over takes the warp's next point at once instead of waiting
+// for the slowest walk of its row.  Lane occupancy rises, but the 32 lanes then work on points of different rows, their node
+// and leaf fetches stop sharing cache lines, and the kernel is bound by exactly those fetches: 63 -> 70 ms.)
+__device__ __forceinline__ void compute_share_nn(const PackedNnScene& s, const float* __restrict__ g, unsigned n, unsigned me, unsigned G,
+                                                 unsigned t_addr, AccT& acc, int* __restrict__ cache, bool use_cache) {
     const unsigned lane = threadIdx.x & 31;
     float T[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) T[i] = lds32(t_addr + 4 * i);
 #pragma unroll 1
-    for (unsigned i = lane; i < n; i += 32) {
+    for (unsigned i = me * 32 + lane; i < n; i += G * 32) {
         float px, py, pz;
         transform(T, __ldg(g + 3 * i), __ldg(g + 3 * i + 1), __ldg(g + 3 * i + 2), px, py, pz);
         Corr c;
@@ -718,7 +725,7 @@ icp_hyp_kernel(const float* __restrict__ pts, size_t capacity_points, const uint
             acc_zero(acc);
             bool odd = false;
             if constexpr (Tr::kProjective) compute_slice(sc, gsl, n_mine, may_overread, t_addr, acc, odd);
-            else compute_slice_nn(sc, gsl, n_mine, t_addr, acc, sc.cache ? sc.cache + ((size_t)offsets[h] + first_pt) : nullptr, pass > 0);
+            else compute_share_nn(sc, pts + 3 * (size_t)offsets[h], n, g, G, t_addr, acc, sc.cache ? sc.cache + (size_t)offsets[h] : nullptr, pass > 0);
             // ---- the warp's 29 sums -> lane l holds sum l
             float v[32];
             acc_unpack(acc, v);

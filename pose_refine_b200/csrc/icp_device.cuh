@@ -248,21 +248,24 @@ __device__ __forceinline__ int nn_search_packed_t(const PackedNnScene& s, float 
     if (COUNT) visits++;
     // a box lower bound is a rounded float, so it is trusted only with a 1e-5 margin
     bool go = box_dist_sq(lo, hi, px, py, pz) * 0.99999f < best;
-    while (go) {
-        const int a = __float_as_int(lo.w);
-        if (a < 0) {
-            const int left = a & 0xFFFFFF, cnt = (a >> 24) & 127;
-            if (COUNT) tests += (unsigned)cnt;
-            for (int i = left; i < left + cnt; i++) {
-                const float4 q = __ldg(s.pts4 + i);
-                const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
-                const float d2 = addf(addf(mulf(dx, dx), mulf(dy, dy)), mulf(dz, dz));    // pcd_scene.h:86-89
-                if (d2 < best) { best = d2; best_i = i; }
-                else if (d2 == best && best_i >= 0 && i != best_i && nn_visited_first(s.ref, px, py, pz, i, best_i)) best_i = i;
+    // next parked subtree that is still within reach -> (lo, hi); false when the stack is exhausted
+    auto pop = [&]() {
+        while (sp > 0) {
+            --sp;
+            if (stack_lb[sp] < best) {
+                const float4* p = (stack_n[sp] < s.n_top) ? s.top + 2 * stack_n[sp] : s.nodes + 2 * stack_n[sp];
+                lo = p[0]; hi = p[1];
+                return true;
             }
-            go = false;
-        } else {
-            const int c1 = a & 0xFFFFFFF;
+        }
+        return false;
+    };
+    // Two phases per round, so that the lanes of a warp scan their leaves TOGETHER: (A) walk internal nodes until the
+    // current node is a leaf, (B) scan it.  With the scan inside the walk loop a lane scanned its leaf while the others were
+    // still descending: the scan -- half of the kernel's instructions -- ran on 4.8 of 32 lanes (ncu, profiles/r02_ncu_icp_nn.txt).
+    while (go) {
+        while (go && __float_as_int(lo.w) >= 0) {
+            const int c1 = __float_as_int(lo.w) & 0xFFFFFFF;
             const float4* p = node_ptr(s, c1);
             const float4 lo1 = p[0], hi1 = p[1], lo2 = p[2], hi2 = p[3];
             if (COUNT) visits += 2;
@@ -273,18 +276,23 @@ __device__ __forceinline__ int nn_search_packed_t(const PackedNnScene& s, float 
                 if (sp < kStack) { stack_n[sp] = first1 ? c1 + 1 : c1; stack_lb[sp] = lb_far; sp++; }
                 else overflow = true;
             }
-            if (lb_near < best) { lo = first1 ? lo1 : lo2; hi = first1 ? hi1 : hi2; continue; }
-            go = false;
+            if (lb_near < best) { lo = first1 ? lo1 : lo2; hi = first1 ? hi1 : hi2; }
+            else go = pop();
         }
-        while (sp > 0) {
-            --sp;
-            if (stack_lb[sp] < best) {
-                const float4* p = (stack_n[sp] < s.n_top) ? s.top + 2 * stack_n[sp] : s.nodes + 2 * stack_n[sp];
-                lo = p[0]; hi = p[1];
-                go = true;
-                break;
+        if (!go) break;
+        {
+            const int a = __float_as_int(lo.w);
+            const int left = a & 0xFFFFFF, cnt = (a >> 24) & 127;
+            if (COUNT) tests += (unsigned)cnt;
+            for (int i = left; i < left + cnt; i++) {
+                const float4 q = __ldg(s.pts4 + i);
+                const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+                const float d2 = addf(addf(mulf(dx, dx), mulf(dy, dy)), mulf(dz, dz));    // pcd_scene.h:86-89
+                if (d2 < best) { best = d2; best_i = i; }
+                else if (d2 == best && best_i >= 0 && i != best_i && nn_visited_first(s.ref, px, py, pz, i, best_i)) best_i = i;
             }
         }
+        go = pop();
     }
     return overflow ? -2 : best_i;
 }
