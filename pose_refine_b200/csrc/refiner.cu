@@ -123,11 +123,12 @@ const char* pr_error_string(int status) {
 }
 
 int pr_device_check(void) {
-    int dev = 0;
+    // attribute query (microseconds), not cudaGetDeviceProperties (milliseconds, and worse with several processes on
+    // the host): every Python entry point calls this first
+    int dev = 0, major = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return PR_ERR_NO_DEVICE; }
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { cudaGetLastError(); return PR_ERR_NO_DEVICE; }
-    return (p.major == 10) ? PR_OK : PR_ERR_NO_DEVICE;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { cudaGetLastError(); return PR_ERR_NO_DEVICE; }
+    return (major == 10) ? PR_OK : PR_ERR_NO_DEVICE;
 }
 
 int pr_device_malloc(void** ptr, size_t bytes) {
