@@ -13,19 +13,18 @@
 // kernel that rewrites every point, another sync.  Here ONE launch runs all passes of all hypotheses.
 //
 // icp_hyp_kernel (the driver that ships): a HYPOTHESIS is owned, for all of its passes, by one thread-block
-// CLUSTER of C CTAs (C = 1, 2, 4 or 8, chosen per launch).  Every warp of the cluster owns a fixed slice of the
-// hypothesis' points.  The slice is brought into the warp's own shared-memory tiles with TMA bulk copies
-// (cp.async.bulk + mbarrier); when it fits the warp's tile ring it is loaded ONCE and stays resident for all 31
-// passes, otherwise it streams through the ring (from L2: nothing else touches those lines in between).  A pass
-// applies the hypothesis' ACCUMULATED 4x4 to the ORIGINAL points on the fly (no write-back, the fusion the
-// reference's notes.md:3 asks for), looks the correspondences up, accumulates the 29 sums in registers -- two
-// points per FFMA2 --, reduces them with a register-transposing warp butterfly, adds the warps of a CTA through
-// shared memory and the CTAs of the cluster through DISTRIBUTED shared memory (one st.shared::cluster per lane
-// and peer, one barrier.cluster per pass), and every CTA then evaluates fitness / rmse / the stop tests exactly
-// as icp.cu:181-194 and solves the 6x6 system redundantly (identical inputs, identical bits) -- no broadcast of
-// the new 4x4, no global-memory flags, no polling, no tickets.  Clusters claim hypotheses from one global
-// counter; two or more CTAs of different clusters share an SM, so the serial reduce -> solve section of one
-// hypothesis overlaps the point pass of another.
+// CLUSTER of C CTAs (C = 2, 4 or 8, chosen per launch).  Every warp of the cluster owns a fixed slice of the
+// hypothesis' points and re-reads it every pass with plain coalesced loads, one group ahead -- from L2, not HBM:
+// nothing else touches those lines between the passes of a hypothesis, and the cluster size is chosen so that the
+// clouds of all hypotheses in flight fit the L2 (pick_cluster).  A pass applies the hypothesis' ACCUMULATED 4x4 to the
+// ORIGINAL points on the fly (no write-back, the fusion the reference's notes.md:3 asks for), looks the correspondences
+// up, accumulates the 29 sums in registers -- two points per FFMA2 --, reduces them with a register-transposing warp
+// butterfly, adds the warps of a CTA through shared memory and the CTAs of the cluster through DISTRIBUTED shared
+// memory (st.async onto the peers' mbarriers, one 4-byte store per lane and peer), and every CTA then evaluates
+// fitness / rmse / the stop tests exactly as icp.cu:181-194 and solves the 6x6 system redundantly (identical inputs,
+// identical bits) -- no broadcast of the new 4x4, no global-memory flags, no polling, no tickets.  Clusters claim
+// hypotheses from one global counter, longest first (icp_order_kernel); several CTAs of different clusters share an
+// SM, so the serial reduce -> solve section of one hypothesis overlaps the point pass of another.
 // (Tried and measured, git history "icp_pipe_kernel": two hypotheses in flight per cluster, every warp alternating between
 // them, the serial section on one warp behind mbarriers only -- the barrier stalls (14 % of warp time) vanish, but either all
 // 512 clouds are in flight at once (135 MB > L2: hit rate 97 % -> 62 %, 1.66 ms) or the clusters must be twice as wide, which
