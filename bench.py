@@ -396,7 +396,7 @@ def run_ours(args):
             _, pts3, off3, cnt3 = r3.buffers(P)
             n3 = int(cnt3.sum().item())
             sn = api.SceneNN().init_cuda(c3_depth, K)
-            stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+            stats = torch.zeros(4, dtype=torch.int64, device="cuda")
             nq = int(cnt3[0].item())
             wsq, wsq_bytes = api._icp_workspace(1, nq, sn)
             snc = sn.c()
@@ -407,7 +407,8 @@ def run_ours(args):
             configs["C3"] = {"workload": f"{P} hypotheses per GPU, kd-tree scene of {n_scene} points / {n_nodes} nodes, 640x480, 31 passes",
                              "scaling": "weak", "value": P * world / (ms3 * 1e-3), "unit": "hypotheses/s", "ms_per_step": ms3,
                              "nn_queries_per_s": (ITERS + 1) * n3 * world / (ms3 * 1e-3),
-                             "node_fetches_per_query_pass0": float(st[0]) / nq, "leaf_points_tested_per_query_pass0": float(st[1]) / nq,
+                             "tree_walk_pass0": {"node_fetches_per_query": float(st[0]) / nq, "leaf_points_tested_per_query": float(st[1]) / nq},
+                             "hash_grid_pass0": {"queries_answered_frac": float(st[2]) / nq, "points_tested_per_query": float(st[3]) / nq},
                              "roofline": {"bound": "hbm", "kernel": "icp_hyp_kernel<PackedNnScene> + render/cloud (whole step)",
                                           "achieved": alg3 / (ms3 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                           "frac": alg3 / (ms3 * 1e-3) / 1e9 / peak, "traffic": None,

@@ -296,8 +296,9 @@ int pr_correspondences_projective(const float* pts_dev, size_t n, const pr_scene
 int pr_correspondences_nn(const float* pts_dev, size_t n, const pr_scene_nn* scene, int32_t* idx_dev,
                           void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
 int pr_solve_666_device(const float* S29_dev, size_t n, int fast, float* E16_dev, pr_stream_t stream);
-/*   pr_nn_walk_stats: cost of the packed kd-tree search over n queries: stats2_dev[0] = nodes fetched (box tests),    */
-/*                    stats2_dev[1] = leaf points tested (uint64 each).  For bench.py's C3 roofline block.               */
+/*   pr_nn_walk_stats: cost of the nearest-neighbour search over n queries, four uint64: stats_dev[0] = tree nodes fetched  */
+/*                    (box tests) and [1] = leaf points tested by the unseeded tree walk; [2] = queries the hash grid      */
+/*                    answers without the tree and [3] = points it tests for them.  For bench.py's C3 block.               */
 int pr_nn_walk_stats(const float* pts_dev, size_t n, const pr_scene_nn* scene, uint64_t* stats2_dev,
                      void* workspace_dev, size_t workspace_bytes, pr_stream_t stream);
 

@@ -594,22 +594,79 @@ __device__ __noinline__ float slow_slice(const PackedScene& s, const float* __re
 // (Tried: lanes as persistent workers -- a lane whose walk is over takes the warp's next point at once instead of waiting
 // for the slowest walk of its row.  Lane occupancy rises, but the 32 lanes then work on points of different rows, their node
 // and leaf fetches stop sharing cache lines, and the kernel is bound by exactly those fetches: 63 -> 70 ms.)
+#ifndef PR_NN_TABLE
+#define PR_NN_TABLE 2
+#endif
+constexpr int kNnQueue = 64;      // per warp: point indices waiting for the tree walk (<= 31 left over + 32 new)
+__device__ __forceinline__ void nn_corr_of(const PackedNnScene& s, int best_i, Corr& c) {
+    const float4 q = __ldg(s.pts4 + best_i);
+    c.qx = q.x; c.qy = q.y; c.qz = q.z;
+    c.nx = __ldg(s.nrm + 3 * best_i); c.ny = __ldg(s.nrm + 3 * best_i + 1); c.nz = __ldg(s.nrm + 3 * best_i + 2);
+}
+// `queue` (shared memory, kNnQueue ints per warp): the grid (nn_grid_query) answers most points at once; the others are
+// compacted into the queue and walked through the tree 32 at a time, so the long walks run on full warps instead of
+// holding up the 30 lanes of their row that were done after a dozen distance tests.
 __device__ __forceinline__ void compute_share_nn(const PackedNnScene& s, const float* __restrict__ g, unsigned n, unsigned me, unsigned G,
-                                                 unsigned t_addr, AccT& acc, int* __restrict__ cache, bool use_cache) {
+                                                 unsigned t_addr, AccT& acc, int* __restrict__ cache, bool use_cache, int* __restrict__ queue) {
     const unsigned lane = threadIdx.x & 31;
-    float T[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) T[i] = lds32(t_addr + 4 * i);
-#pragma unroll 1
-    for (unsigned i = me * 32 + lane; i < n; i += G * 32) {
-        float px, py, pz;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // the accumulated transform stays in shared memory (three LDS.128 per point): the walk needs the registers
+    auto xform = [&](unsigned i, float& px, float& py, float& pz) {
+        const float4 r0 = lds128(t_addr), r1 = lds128(t_addr + 16), r2 = lds128(t_addr + 32);
+        const float T[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
         transform(T, __ldg(g + 3 * i), __ldg(g + 3 * i + 1), __ldg(g + 3 * i + 2), px, py, pz);
-        Corr c;
-        int found;
-        const int hint = (cache && use_cache) ? cache[i] : -1;
-        if (query(s, px, py, pz, c, hint, found)) acc_add(acc, px, py, pz, c);
-        if (cache) cache[i] = found;
+    };
+    NnGridParams gp;
+    gp.enabled = 0u;
+    if (s.grid.params && s.nodes) gp = *s.grid.params;
+    unsigned qn = 0;
+    // the tree walk of the first `count` (<= 32) queued points
+    auto drain = [&](unsigned count) {
+        if (lane < count) {
+            const unsigned i = (unsigned)queue[lane];
+            float px, py, pz;
+            xform(i, px, py, pz);
+            Corr c;
+            int found;
+            const int hint = (cache && use_cache) ? cache[i] : -1;
+            if (query(s, px, py, pz, c, hint, found)) acc_add(acc, px, py, pz, c);
+            if (cache) cache[i] = found;
+        }
+        __syncwarp();
+        if (qn > 32) {
+            int t = 0;
+            if (lane + 32 < qn) t = queue[lane + 32];
+            __syncwarp();
+            if (lane + 32 < qn) queue[lane] = t;
+            __syncwarp();
+        }
+        qn -= count;
+    };
+#pragma unroll 1
+    for (unsigned base = me * 32; base < n; base += G * 32) {
+        const unsigned i = base + lane;
+        bool walk = false;
+        if (i < n) {
+            float px, py, pz;
+            xform(i, px, py, pz);
+            int best_i;
+            unsigned tests = 0;
+            if (gp.enabled && nn_grid_query<false>(s, gp, px, py, pz, best_i, tests)) {
+                Corr c;
+                nn_corr_of(s, best_i, c);
+                acc_add(acc, px, py, pz, c);
+                if (cache) cache[i] = best_i;
+            } else {
+                walk = true;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, walk);
+        if (walk) queue[qn + __popc(m & lt_mask)] = (int)i;
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) drain(32);
     }
+    if (qn) drain(qn);
 }
 
 // a foreign kd-tree the packed encoding cannot hold (flag raised by nn_pack_nodes_kernel): walk the reference layout
@@ -623,7 +680,7 @@ template <class SceneT> struct HypTraits {
     static constexpr int kWarps = kProjective ? PR_HYP_WARPS : PR_NN_WARPS;
     static constexpr int kMinBlocks = kProjective ? PR_HYP_MINB : PR_NN_MINB;
     using Acc = typename std::conditional<kProjective, AccP, AccT>::type;
-    static constexpr size_t kExtraSmem = kProjective ? 0 : (size_t)kTopNodes * 32;     // top levels of the kd-tree
+    static constexpr size_t kExtraSmem = kProjective ? 0 : (size_t)kTopNodes * 32 + (size_t)kWarps * kNnQueue * 4;     // top levels of the kd-tree + the warps' walk queues
 };
 // dynamic shared memory of a CTA: state | sums | spare | mbarriers | per-warp partials | cluster slots (2 parities) | tree top
 template <int kWarps> __host__ __device__ constexpr size_t hyp_fixed_smem() { return 64 + 128 + 64 + 64 + (size_t)kWarps * 128 + 2 * kMaxCluster * 128; }
@@ -752,7 +809,8 @@ icp_hyp_kernel(const float* __restrict__ pts, size_t capacity_points, const uint
             acc_zero(acc);
             bool odd = false;
             if constexpr (Tr::kProjective) compute_slice(sc, gsl, n_mine, may_overread, t_addr, acc, odd);
-            else compute_share_nn(sc, pts + 3 * (size_t)offsets[h], n, g, G, t_addr, acc, sc.cache ? sc.cache + (size_t)offsets[h] : nullptr, pass > 0);
+            else compute_share_nn(sc, pts + 3 * (size_t)offsets[h], n, g, G, t_addr, acc, sc.cache ? sc.cache + (size_t)offsets[h] : nullptr, pass > 0,
+                                  reinterpret_cast<int*>(smem_raw + (extra0 - smem0) + kTopNodes * 32) + warp * kNnQueue);
             // ---- the warp's 29 sums -> lane l holds sum l
             float v[32];
             acc_unpack(acc, v);
@@ -864,8 +922,18 @@ corr_nn_kernel(const float* __restrict__ pts, unsigned n, PackedNnScene s, int* 
     const unsigned i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const float px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
-    int b = (s.unsupported && *s.unsupported) ? -2 : nn_search_packed(s, px, py, pz);
-    if (b == -2) b = nn_search_reference(s.ref, px, py, pz);
+    const bool packed_ok = !(s.unsupported && *s.unsupported);
+    int b = -2;
+    unsigned tests = 0;
+    bool done = false;
+    if (packed_ok && s.grid.params) {            // the grid first, exactly as compute_share_nn decides
+        const NnGridParams gp = *s.grid.params;
+        done = gp.enabled && nn_grid_query<false>(s, gp, px, py, pz, b, tests);
+    }
+    if (!done) {
+        b = packed_ok ? nn_search_packed(s, px, py, pz) : -2;
+        if (b == -2) b = nn_search_reference(s.ref, px, py, pz);
+    }
     out_idx[i] = b < 0 ? -1 : b;
 }
 
@@ -873,10 +941,21 @@ corr_nn_kernel(const float* __restrict__ pts, unsigned n, PackedNnScene s, int* 
 __global__ void __launch_bounds__(256)
 walk_stats_kernel(const float* __restrict__ pts, unsigned n, PackedNnScene s, unsigned long long* __restrict__ stats) {
     const unsigned i = blockIdx.x * 256 + threadIdx.x;
-    unsigned v = 0, t = 0;
-    if (i < n) nn_search_packed_t<true>(s, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], v, t);
+    unsigned v = 0, t = 0, r = 0, gt = 0;
+    if (i < n) {
+        nn_search_packed_t<true>(s, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], v, t);
+        if (s.grid.params) {
+            const NnGridParams gp = *s.grid.params;
+            int b;
+            r = (gp.enabled && nn_grid_query<true>(s, gp, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], b, gt)) ? 1u : 0u;
+        }
+    }
     v = __reduce_add_sync(0xffffffffu, v); t = __reduce_add_sync(0xffffffffu, t);
-    if ((threadIdx.x & 31) == 0) { atomicAdd(stats, (unsigned long long)v); atomicAdd(stats + 1, (unsigned long long)t); }
+    r = __reduce_add_sync(0xffffffffu, r); gt = __reduce_add_sync(0xffffffffu, gt);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(stats, (unsigned long long)v); atomicAdd(stats + 1, (unsigned long long)t);
+        atomicAdd(stats + 2, (unsigned long long)r); atomicAdd(stats + 3, (unsigned long long)gt);
+    }
 }
 
 __global__ void __launch_bounds__(64)
@@ -1111,6 +1190,91 @@ inline int pack_tree(const NnScene& s, size_t n_points, const PackedTree& t, cud
     return PR_OK;
 }
 
+// the hash grid (icp_device.cuh) lives behind the packed tree, when the workspace has room for it
+struct GridWs {
+    NnGridParams* params; uint2* table; unsigned* keys; unsigned* counts; unsigned* cursor; unsigned* pt_slot; float4* gpts;
+    unsigned log2_slots;
+    size_t bytes;
+};
+inline GridWs carve_grid(void* base, size_t n_points) {
+    GridWs g;
+    // 8 n block memberships in about n / 3 distinct blocks for a sampled surface (2 n slots: a sixth full); a scene of
+    // isolated points (up to 8 n blocks) overfills the table, which the count kernel notices and answers by switching the
+    // grid off (the tree then answers everything)
+    unsigned lg = 10;
+    while (lg < 28 && ((size_t)1 << lg) < PR_NN_TABLE * n_points) lg++;
+    g.log2_slots = lg;
+    const size_t slots = (size_t)1 << lg;
+    char* w = (char*)base;
+    size_t used = 0;
+    auto take = [&](size_t bytes) { char* p = w + used; used += icp_align_up(bytes, 256); return p; };
+    g.params = (NnGridParams*)take(sizeof(NnGridParams));
+    g.table = (uint2*)take(slots * 8);
+    g.keys = (unsigned*)take(slots * 4);
+    g.counts = (unsigned*)take(slots * 4);
+    g.cursor = (unsigned*)take(slots * 4);
+    g.pt_slot = (unsigned*)take(8 * n_points * 4);
+    g.gpts = (float4*)take(8 * n_points * 16);
+    g.bytes = used;
+    return g;
+}
+inline int build_grid(const PackedTree& t, size_t n_points, int n_nodes, const GridWs& g, cudaStream_t stream) {
+    const size_t slots = (size_t)1 << g.log2_slots;
+    PR_CUDA_TRY(cudaMemsetAsync(g.keys, 0xFF, slots * 4, stream));
+    PR_CUDA_TRY(cudaMemsetAsync(g.counts, 0, slots * 4, stream));
+    nn_grid_params_kernel<<<1, 256, 0, stream>>>(t.nodes, n_nodes, (unsigned)n_points, g.log2_slots, t.flag, g.params);
+    const unsigned blocks = (unsigned)((8 * n_points + 255) / 256);
+    nn_grid_count_kernel<<<blocks, 256, 0, stream>>>(t.pts4, (unsigned)n_points, g.params, g.keys, g.counts, g.pt_slot);
+    nn_grid_scan_kernel<<<1, 1024, 0, stream>>>(g.keys, g.counts, (unsigned)slots, g.cursor, g.table);
+    nn_grid_fill_kernel<<<blocks, 256, 0, stream>>>(t.pts4, (unsigned)n_points, g.params, g.pt_slot, g.cursor, g.gpts);
+    count_launch(4);
+    return PR_OK;
+}
+// packed scene of a kd-tree scene inside `region` (region_bytes): packed tree always, the grid when it fits
+inline void init_packed_nn(const NnScene& s, PackedNnScene& ps) {        // nothing packed: the kernel walks the reference layout
+    ps.max_dist_sq = s.max_dist_sq; ps.nrm = s.nrm; ps.n_nodes = s.n_nodes; ps.ref = s;
+    ps.nodes = nullptr; ps.pts4 = nullptr; ps.unsupported = nullptr; ps.top = nullptr; ps.n_top = 0; ps.cache = nullptr;
+    ps.grid.params = nullptr; ps.grid.table = nullptr; ps.grid.gpts = nullptr;
+}
+inline int make_packed_nn(const NnScene& s, const pr_scene_nn* scene, float4* region, size_t region_bytes, PackedNnScene& ps, cudaStream_t stream) {
+    init_packed_nn(s, ps);
+    if (s.n_nodes <= 0) return PR_OK;
+    const size_t tree_bytes = icp_align_up((scene->n_points + 2 * scene->n_nodes) * 16 + 4, 256);
+    if (region_bytes < tree_bytes) return PR_ERR_WORKSPACE_TOO_SMALL;
+    const PackedTree t = carve_packed_tree(region, scene->n_points, scene->n_nodes);
+    int rc = pack_tree(s, scene->n_points, t, stream);
+    if (rc != PR_OK) return rc;
+    ps.nodes = t.nodes; ps.pts4 = t.pts4; ps.unsupported = t.flag;
+    if (scene->n_points > 0 && scene->n_points < (1u << 21)) {      // 8 n list entries behind a 24-bit start
+        const GridWs g = carve_grid((char*)region + tree_bytes, scene->n_points);
+        if (tree_bytes + g.bytes <= region_bytes) {
+            rc = build_grid(t, scene->n_points, s.n_nodes, g, stream);
+            if (rc != PR_OK) return rc;
+            ps.grid.params = g.params; ps.grid.table = g.table; ps.grid.gpts = g.gpts;
+        }
+    }
+    return PR_OK;
+}
+// float4-pairs ("scene pixels" of carve_icp_ws, 32 bytes each) a kd-tree scene needs: packed tree + grid
+inline size_t nn_scene_units(size_t n_points, size_t n_nodes) {
+    const size_t tree_bytes = icp_align_up((n_points + 2 * n_nodes) * 16 + 4, 256);
+    return (tree_bytes + carve_grid(nullptr, n_points).bytes + 31) / 32 + 16;
+}
+// workspace layout for a kd-tree scene, the richest that fits: grid + search cache, grid, cache, neither
+// (pr_icp_nn_workspace_bytes has room for everything; a workspace sized by pr_icp_workspace_bytes still works)
+inline bool carve_nn_ws(void* base, size_t bytes, size_t n_hyp, size_t capacity_points, const pr_scene_nn* scene, bool want_cache,
+                        IcpWs& ws, size_t& region_bytes) {
+    const size_t full = nn_scene_units(scene->n_points, scene->n_nodes), small = scene->n_points + 2 * scene->n_nodes + 16;
+    const size_t units[4] = {full, full, small, small};
+    const bool cache[4] = {true, false, true, false};
+    for (int k = 0; k < 4; k++) {
+        if (cache[k] && !want_cache) continue;
+        ws = carve_icp_ws(base, n_hyp, capacity_points, units[k], cache[k]);
+        if (ws.bytes <= bytes) { region_bytes = units[k] * 32; return true; }
+    }
+    return false;
+}
+
 // single cloud, identity transform, one reduction pass -> out29 (parity / debug entry point).  FAST: through the
 // shipped driver (criteria (0,0,0): one evaluation pass; the sums of pass 0 are copied out), else the reference-arithmetic kernel.
 template <class SceneT>
@@ -1155,7 +1319,7 @@ size_t pr_icp_workspace_bytes(size_t n_hyp, size_t capacity_points, size_t scene
 }
 
 size_t pr_icp_nn_workspace_bytes(size_t n_hyp, size_t capacity_points, size_t n_scene_points, size_t n_nodes) {
-    return carve_icp_ws(nullptr, n_hyp, capacity_points, n_scene_points + 2 * n_nodes + 16, true).bytes;
+    return carve_icp_ws(nullptr, n_hyp, capacity_points, nn_scene_units(n_scene_points, n_nodes), true).bytes;
 }
 
 size_t pr_scene_projective_packed_bytes(uint32_t width, uint32_t height) { return (size_t)width * height * 32; }
@@ -1232,20 +1396,19 @@ int pr_icp_nn_batch(float* pts_dev, const uint32_t* offsets_dev, const uint32_t*
     // encoding.  No tree KDTree_cpu::build_tree / pr_scene_nn_build* produce has them (leaf <= max_leaf, children appended
     // together); a foreign tree that does is detected by the packing kernel, which then marks the packed root as an empty
     // leaf-less tree and the kernel walks the reference layout instead -- decided on the device, no host round trip.
-    const size_t units = scene->n_points + 2 * scene->n_nodes + 16;
-    // with room for one int per model point (pr_icp_nn_workspace_bytes) every pass starts its searches from the previous
-    // pass' winners; a workspace sized by pr_icp_workspace_bytes still works, without that
-    IcpWs ws = carve_icp_ws(workspace_dev, n_hyp, capacity_points, units, true);
-    if (workspace_bytes < ws.bytes) ws = carve_icp_ws(workspace_dev, n_hyp, capacity_points, units, false);
-    if (workspace_bytes < ws.bytes) return PR_ERR_WORKSPACE_TOO_SMALL;
+    // with room for one int per model point (pr_icp_nn_workspace_bytes) every pass starts its tree walks from the previous
+    // pass' winners, and with room for the hash grid most points never walk the tree at all; a workspace sized by
+    // pr_icp_workspace_bytes still works, without either
+    IcpWs ws;
+    size_t region_bytes = 0;
+    if (!carve_nn_ws(workspace_dev, workspace_bytes, n_hyp, capacity_points, scene, true, ws, region_bytes)) return PR_ERR_WORKSPACE_TOO_SMALL;
     PackedNnScene ps;
-    ps.max_dist_sq = s.max_dist_sq; ps.nrm = s.nrm; ps.n_nodes = s.n_nodes; ps.ref = s;
-    ps.nodes = nullptr; ps.pts4 = nullptr; ps.unsupported = nullptr; ps.top = nullptr; ps.n_top = 0; ps.cache = nullptr;
-    if (!(flags & PR_ICP_REFERENCE_ARITHMETIC) && s.n_nodes > 0) {
-        const PackedTree t = carve_packed_tree(ws.packed, scene->n_points, scene->n_nodes);
-        rc = pack_tree(s, scene->n_points, t, stream);
+    if (!(flags & PR_ICP_REFERENCE_ARITHMETIC)) {
+        rc = make_packed_nn(s, scene, ws.packed, region_bytes, ps, stream);
         if (rc != PR_OK) return rc;
-        ps.nodes = t.nodes; ps.pts4 = t.pts4; ps.unsupported = t.flag; ps.cache = ws.nn_cache;
+        if (ps.nodes) ps.cache = ws.nn_cache;
+    } else {
+        init_packed_nn(s, ps);
     }
     return run_icp(pts_dev, offsets_dev, counts_dev, n_hyp, capacity_points, s, ps, criteria, results_dev, flags, ws, stream);
 }
@@ -1301,21 +1464,16 @@ int pr_pass_sums_nn(const float* pts_dev, const uint32_t* offsets_dev, const uin
     pr_icp_criteria crit = {0.f, 0.f, 0};
     if (!out32_dev) return PR_ERR_INVALID_ARGUMENT;
     if (n_hyp == 0) return PR_OK;
-    const size_t units = scene->n_points + 2 * scene->n_nodes + 16;
-    IcpWs ws = carve_icp_ws(workspace_dev, n_hyp, capacity_points, units);
+    if (!workspace_dev) return PR_ERR_INVALID_ARGUMENT;
+    IcpWs ws;
+    size_t region_bytes = 0;
+    if (!carve_nn_ws(workspace_dev, workspace_bytes, n_hyp, capacity_points, scene, false, ws, region_bytes)) return PR_ERR_WORKSPACE_TOO_SMALL;
     rc = check_icp_args(pts_dev, offsets_dev, counts_dev, n_hyp, capacity_points, crit, (pr_registration_result*)ws.state, workspace_dev);
     if (rc != PR_OK) return rc;
-    if (workspace_bytes < ws.bytes) return PR_ERR_WORKSPACE_TOO_SMALL;
     cudaStream_t stream = as_stream(stream_);
     PackedNnScene ps;
-    ps.max_dist_sq = s.max_dist_sq; ps.nrm = s.nrm; ps.n_nodes = s.n_nodes; ps.ref = s;
-    ps.nodes = nullptr; ps.pts4 = nullptr; ps.unsupported = nullptr; ps.top = nullptr; ps.n_top = 0; ps.cache = nullptr;
-    if (s.n_nodes > 0) {
-        const PackedTree t = carve_packed_tree(ws.packed, scene->n_points, scene->n_nodes);
-        rc = pack_tree(s, scene->n_points, t, stream);
-        if (rc != PR_OK) return rc;
-        ps.nodes = t.nodes; ps.pts4 = t.pts4; ps.unsupported = t.flag;
-    }
+    rc = make_packed_nn(s, scene, ws.packed, region_bytes, ps, stream);
+    if (rc != PR_OK) return rc;
     rc = launch_hyp(pts_dev, capacity_points, offsets_dev, counts_dev, n_hyp, ws, ps, crit, (pr_registration_result*)ws.state,
                     out32_dev, 0, stream);
     if (rc != PR_OK) return rc;
@@ -1350,15 +1508,12 @@ int pr_correspondences_nn(const float* pts_dev, size_t n, const pr_scene_nn* sce
     if (n == 0) return PR_OK;
     cudaStream_t stream = as_stream(stream_);
     if (s.n_nodes == 0) { PR_CUDA_TRY(cudaMemsetAsync(idx_dev, 0xFF, n * 4, stream)); return PR_OK; }
-    const size_t units = scene->n_points + 2 * scene->n_nodes + 16;
-    IcpWs ws = carve_icp_ws(workspace_dev, 1, n, units);
-    if (workspace_bytes < ws.bytes) return PR_ERR_WORKSPACE_TOO_SMALL;
-    const PackedTree t = carve_packed_tree(ws.packed, scene->n_points, scene->n_nodes);
-    rc = pack_tree(s, scene->n_points, t, stream);
-    if (rc != PR_OK) return rc;
+    IcpWs ws;
+    size_t region_bytes = 0;
+    if (!carve_nn_ws(workspace_dev, workspace_bytes, 1, n, scene, false, ws, region_bytes)) return PR_ERR_WORKSPACE_TOO_SMALL;
     PackedNnScene ps;
-    ps.max_dist_sq = s.max_dist_sq; ps.nrm = s.nrm; ps.n_nodes = s.n_nodes; ps.ref = s;
-    ps.nodes = t.nodes; ps.pts4 = t.pts4; ps.unsupported = t.flag; ps.top = nullptr; ps.n_top = 0; ps.cache = nullptr;
+    rc = make_packed_nn(s, scene, ws.packed, region_bytes, ps, stream);
+    if (rc != PR_OK) return rc;
     corr_nn_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pts_dev, (unsigned)n, ps, idx_dev);
     count_launch();
     PR_LAUNCH_CHECK();
@@ -1372,17 +1527,14 @@ int pr_nn_walk_stats(const float* pts_dev, size_t n, const pr_scene_nn* scene, u
     if (rc != PR_OK) return rc;
     if (!pts_dev || !stats2_dev || !workspace_dev || n > 0x7FFFFFFFull || s.n_nodes == 0) return PR_ERR_INVALID_ARGUMENT;
     cudaStream_t stream = as_stream(stream_);
-    PR_CUDA_TRY(cudaMemsetAsync(stats2_dev, 0, 16, stream));
+    PR_CUDA_TRY(cudaMemsetAsync(stats2_dev, 0, 32, stream));
     if (n == 0) return PR_OK;
-    const size_t units = scene->n_points + 2 * scene->n_nodes + 16;
-    IcpWs ws = carve_icp_ws(workspace_dev, 1, n, units);
-    if (workspace_bytes < ws.bytes) return PR_ERR_WORKSPACE_TOO_SMALL;
-    const PackedTree t = carve_packed_tree(ws.packed, scene->n_points, scene->n_nodes);
-    rc = pack_tree(s, scene->n_points, t, stream);
-    if (rc != PR_OK) return rc;
+    IcpWs ws;
+    size_t region_bytes = 0;
+    if (!carve_nn_ws(workspace_dev, workspace_bytes, 1, n, scene, false, ws, region_bytes)) return PR_ERR_WORKSPACE_TOO_SMALL;
     PackedNnScene ps;
-    ps.max_dist_sq = s.max_dist_sq; ps.nrm = s.nrm; ps.n_nodes = s.n_nodes; ps.ref = s;
-    ps.nodes = t.nodes; ps.pts4 = t.pts4; ps.unsupported = t.flag; ps.top = nullptr; ps.n_top = 0; ps.cache = nullptr;
+    rc = make_packed_nn(s, scene, ws.packed, region_bytes, ps, stream);
+    if (rc != PR_OK) return rc;
     walk_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pts_dev, (unsigned)n, ps, reinterpret_cast<unsigned long long*>(stats2_dev));
     count_launch();
     PR_LAUNCH_CHECK();

@@ -42,35 +42,43 @@ def summary(rep, out, title):
     open(os.path.join(P, out), "w").write(f"# {title}\n# ncu --set full --clock-control none --import-source on (scripts/gpu_profiles.sh); B200, one launch\n\n" + txt + seg_txt)
     print("wrote", out)
 
-summary("r02_icp_hyp.ncu-rep", "r02_ncu_icp_hyp.txt", "icp_hyp_kernel<PackedScene>: C2, 512 hypotheses x 31 passes, cluster size 2 (scripts/time_icp.py)")
-summary("r02_raster_tile.ncu-rep", "r02_ncu_raster_tile.txt", "raster_tile_kernel: C2, 512 poses of obj_06, clustered path (scripts/time_step.py)")
-summary("r02_icp_nn.ncu-rep", "r02_ncu_icp_nn.txt", "icp_hyp_kernel<PackedNnScene>: C3, 512 hypotheses x 31 passes against the 99k-point kd-tree (scripts/time_nn.py)")
+def main():
+    summary("r02_icp_hyp.ncu-rep", "r02_ncu_icp_hyp.txt", "icp_hyp_kernel<PackedScene>: C2, 512 hypotheses x 31 passes, cluster size 2 (scripts/time_icp.py)")
+    summary("r02_raster_tile.ncu-rep", "r02_ncu_raster_tile.txt", "raster_tile_kernel: C2, 512 poses of obj_06, clustered path (scripts/time_step.py)")
+    summary("r02_icp_nn.ncu-rep", "r02_ncu_icp_nn.txt", "icp_hyp_kernel<PackedNnScene>: C3, 512 hypotheses x 31 passes against the 99k-point kd-tree (scripts/time_nn.py)")
 
-# ---- launch list of the bench command
-rows = list(csv.reader(open(os.path.join(G, "r02_launches_bench.csv"), errors="ignore")))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
-hdr = rows[hi]; ix = {h: i for i, h in enumerate(hdr)}
-launches = []
-for r in rows[hi + 1:]:
-    if len(r) < len(hdr) or r[ix["Metric Name"]] != "gpu__time_duration.sum": continue
-    v = float(r[ix["Metric Value"]].replace(",", "")); u = r[ix["Metric Unit"]]
-    v = v / 1000 if u == "ns" else v * 1000 if u == "ms" else v
-    launches.append((r[ix["Kernel Name"]].split("(")[0].replace("void ", ""), v))
-# the refiner steps: vertex_kernel ... icp_hyp_kernel groups; take the LAST complete step before the stage timings
-names = [n for n, _ in launches]
-step_end = max(i for i, n in enumerate(names[:len(names)]) if "icp_hyp_kernel" in n and i > 0 and "cloud_fill_tiles" in names[i - 1])
-step_start = max(i for i in range(step_end) if "vertex_kernel" in names[i])
-step = launches[step_start:step_end + 1]
-tot = sum(v for _, v in step)
-with open(os.path.join(P, "r02_launches_bench.md"), "w") as f:
-    f.write("# Round 2 -- launch list of `python bench.py --steps 2 --warmup 3 --no-cpu --no-configs`\n\n"
-            "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` (cold-cache, serialised: compare SHARES, not absolutes).\n\n"
-            "## one refiner step (pr_refiner_run_device), in launch order\n\n| kernel | us | share of the step |\n|---|---:|---:|\n")
-    for n, v in step: f.write(f"| {n} | {v:.1f} | {100 * v / tot:.1f}% |\n")
-    f.write(f"\nTotal {tot:.1f} us in {len(step)} launches (+ 2 memsets).  Live in bench.py (CUDA events inside the timed steps): ICP 1.43 ms of a 2.56 ms step = 56 %; "
-            f"here {100 * step[-1][1] / tot:.1f} %.\n\n## all launches of the capture, aggregated\n\n| kernel | launches | total us | mean us |\n|---|---:|---:|---:|\n")
-    agg = collections.OrderedDict()
-    for n, v in launches:
-        a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += v
-    for k, a in agg.items(): f.write(f"| {k} | {a[0]} | {a[1]:.1f} | {a[1] / a[0]:.1f} |\n")
-print(open(os.path.join(P, "r02_launches_bench.md")).read()[:1800])
+    # ---- launch list of the bench command
+    rows = list(csv.reader(open(os.path.join(G, "r02_launches_bench.csv"), errors="ignore")))
+    hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    hdr = rows[hi]; ix = {h: i for i, h in enumerate(hdr)}
+    launches = []
+    for r in rows[hi + 1:]:
+        if len(r) < len(hdr) or r[ix["Metric Name"]] != "gpu__time_duration.sum": continue
+        v = float(r[ix["Metric Value"]].replace(",", "")); u = r[ix["Metric Unit"]]
+        v = v / 1000 if u == "ns" else v * 1000 if u == "ms" else v
+        launches.append((r[ix["Kernel Name"]].split("(")[0].replace("void ", ""), v))
+    # the refiner steps: vertex_kernel ... icp_hyp_kernel groups; take the LAST complete step before the stage timings
+    names = [n for n, _ in launches]
+    step_end = max(i for i, n in enumerate(names[:len(names)]) if "icp_hyp_kernel" in n and i > 0 and "cloud_fill_tiles" in names[i - 1])
+    step_start = max(i for i in range(step_end) if "vertex_kernel" in names[i])
+    step = launches[step_start:step_end + 1]
+    tot = sum(v for _, v in step)
+    with open(os.path.join(P, "r02_launches_bench.md"), "w") as f:
+        f.write("# Round 2 -- launch list of `python bench.py --steps 2 --warmup 3 --no-cpu --no-configs`\n\n"
+                "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` (cold-cache, serialised: compare SHARES, not absolutes).\n\n"
+                "## one refiner step (pr_refiner_run_device), in launch order\n\n| kernel | us | share of the step |\n|---|---:|---:|\n")
+        for n, v in step: f.write(f"| {n} | {v:.1f} | {100 * v / tot:.1f}% |\n")
+        f.write(f"\nTotal {tot:.1f} us in {len(step)} launches (+ 2 memsets).  Live in bench.py (CUDA events inside the timed steps): ICP 1.43 ms of a 2.56 ms step = 56 %; "
+                f"here {100 * step[-1][1] / tot:.1f} %.\n\n## all launches of the capture, aggregated\n\n| kernel | launches | total us | mean us |\n|---|---:|---:|---:|\n")
+        agg = collections.OrderedDict()
+        for n, v in launches:
+            a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += v
+        for k, a in agg.items(): f.write(f"| {k} | {a[0]} | {a[1]:.1f} | {a[1] / a[0]:.1f} |\n")
+    print(open(os.path.join(P, "r02_launches_bench.md")).read()[:1800])
+
+
+if __name__ == "__main__":
+    if len(sys.argv) == 4:      # python scripts/collect_profiles_r02.py <rep in gpurun_out> <out file in profiles/> <title>
+        summary(sys.argv[1], sys.argv[2], sys.argv[3])
+    else:
+        main()

@@ -459,9 +459,10 @@ def test_correspondences_projective_match_the_oracle_point_by_point(api, port, m
 
 
 def test_correspondences_nn_match_the_oracle_point_by_point(api, port, mesh, fixture_scene, golden):
-    """The packed kd-tree search of the hot loop against Scene_nn::query (pcd_scene.h:61-136), index by index: the
-    fixture scene, a 100k-point composited scene (C3) and a fronto-parallel patch full of exact distance ties.
-    Pinned: 0 mismatches (the packed walk keeps the reference's visiting order and strict-< rule, so ties agree too)."""
+    """The nearest-neighbour search of the hot loop (hash grid first, packed kd-tree walk otherwise) against
+    Scene_nn::query (pcd_scene.h:61-136), index by index: the fixture scene, a 100k-point composited scene (C3), a
+    fronto-parallel patch full of exact distance ties (far queries: tree; queries on the plane: grid) and a scene the grid
+    gives up on.  Pinned: 0 mismatches (ties are put in the reference's visiting order explicitly)."""
     arrays, _ = golden
     K = arrays["K"]
     pts, offsets, counts = _hyp8_clouds(api, mesh, arrays)
@@ -471,9 +472,20 @@ def test_correspondences_nn_match_the_oracle_point_by_point(api, port, mesh, fix
     flat[100:380, 120:520] = 300                       # every pixel at the same depth: a lattice of equidistant points
     lattice = port.depth2cloud(flat, K)[::7].copy()
     lattice[:, 2] += np.float32(0.004)                 # queries in front of the lattice, many exactly between points
+    # hash-grid path (icp_device.cuh): queries ON the lattice plane, half of them exactly midway between two lattice points
+    # (exact ties nearer than the grid's radius), the rest a hair off the points themselves
+    on_plane = port.depth2cloud(flat, K)
+    mid = (on_plane[:-1] + on_plane[1:]) * np.float32(0.5)
+    near = np.concatenate([mid[::5], on_plane[::9] + np.float32(1e-5)]).astype(np.float32)
+    # a scene the grid cannot hold: one image row = points on a line (zero-area leaves -> cells of extent / 1019 -> every point
+    # alone in its 8 blocks -> the table overflows and the grid switches itself off; the tree answers)
+    line = np.zeros((480, 640), np.int32)
+    line[240, 20:620] = 400
+    line_pts = port.depth2cloud(line, K)
     scenes = [("fixture", fixture_scene["scene_depth"], clouds),
               ("c3-100k", wl.plane_scene_depth(fixture_scene["scene_depth"], 100000), clouds[:2]),
-              ("tie-rich", flat, [lattice, _moved(lattice, 5)])]
+              ("tie-rich", flat, [lattice, _moved(lattice, 5), near]),
+              ("line", line, [line_pts + np.float32(2e-4), (line_pts[:-1] + line_pts[1:]) * np.float32(0.5)])]
     total = mismatches = 0
     for name, depth, qs in scenes:
         sn = api.SceneNN().init_cuda(depth, K)
