@@ -371,7 +371,7 @@ def run_ours(args):
         # the roofline of the line: the ICP call as it ran INSIDE the K timed steps (mean of the refiner's own events)
         roofline = roofline_block(live_icp_ms, n_pts, P, W, H, "C2",
                                   f"mean over the {live_runs} timed steps of the CUDA events pr_refiner records on the launch stream around its ICP "
-                                  "call (scene packed once per scene; memset of the claim counter + the kernel)")
+                                  "call (scene packed once per scene; the claim-order kernel + the ICP kernel)")
         stage = {"render_cloud_ms": live_render_ms, "icp_ms": live_icp_ms, "runs": live_runs, "icp_ms_alone_l2_flushed": ms_icp_alone,
                  "model_points": n_pts, "setup_ms_one_time": setup_ms,
                  "note": "per-stage means over the timed steps (pr_refiner_stage_ms); icp_ms_alone: the same call timed by itself, "
