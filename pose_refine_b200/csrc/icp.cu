@@ -603,6 +603,9 @@ __device__ __forceinline__ void nn_corr_of(const PackedNnScene& s, int best_i, C
     c.qx = q.x; c.qy = q.y; c.qz = q.z;
     c.nx = __ldg(s.nrm + 3 * best_i); c.ny = __ldg(s.nrm + 3 * best_i + 1); c.nz = __ldg(s.nrm + 3 * best_i + 2);
 }
+// (Tried: the 29 running sums in shared memory instead of registers -- the walk then compiles without its 316 bytes of spills
+// and 5 or 6 CTAs fit an SM, but 30 KB of shared memory per CTA come out of the L1 the walk lives in: 56 -> 61 ms at 4 CTAs
+// per SM, 63 ms at 5, 72 ms at 6.  L1 capacity, not occupancy, is what this kernel is short of.)
 // `queue` (shared memory, kNnQueue ints per warp): the grid (nn_grid_query) answers most points at once; the others are
 // compacted into the queue and walked through the tree 32 at a time, so the long walks run on full warps instead of
 // holding up the 30 lanes of their row that were done after a dozen distance tests.
