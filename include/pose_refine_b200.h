@@ -186,7 +186,8 @@ int pr_raw2depth_mask(const int32_t* raw_dev, size_t n, uint16_t* depth_dev, uin
 /* Offsets are rounded up to a multiple of `align_points` (use 4 for 16-byte aligned clouds).    */
 /* stride must be 1 (stride > 1 indexes out of bounds upstream, icp.cpp:77-82).                  */
 /*   step 1 (count):  counts_dev[n_images], offsets_dev[n_images + 1] (last = total, padded).    */
-/*                    capacity_points (0 = unlimited): a cloud that would end beyond it is        */
+/*                    capacity_points (0 = unlimited, in both steps; offsets are 32-bit, so 2^32-1 */
+/*                    points bound a batch in any case): a cloud that would end beyond it is      */
 /*                    emptied (counts[i] = 0) and *overflow_dev (nullable) is set to 1, so the    */
 /*                    fill step and ICP stay in bounds without a host round trip.                 */
 /*   step 2 (fill):   writes the points of every cloud that fits.                                 */
@@ -339,6 +340,10 @@ int pr_refiner_buffers(pr_refiner* r, const int32_t** depth_dev, const float** p
 /* and the device copy of the results of the last pr_refiner_run (host variant).  Any pointer may be NULL.               */
 int pr_refiner_scene_buffers(pr_refiner* r, const float** scene_pcd_dev, const float** scene_normal_dev,
                              const pr_registration_result** results_dev);
+/* The device-resident run cannot return PR_ERR_CAPACITY (no host round trip): hypotheses whose clouds did not fit           */
+/* capacity_points come back with fitness 0 and the identity transform, and *flag_dev (one uint32 on the device, valid after */
+/* the run completes on its stream) is 1.  pr_refiner_run reads the same flag and returns PR_ERR_CAPACITY.                   */
+int pr_refiner_overflow_flag(pr_refiner* r, const uint32_t** flag_dev);
 /* Device time of the two stages of the runs since the last call (at most the last 256), from CUDA events the refiner      */
 /* records on the caller's stream around the fused render -> cloud call and around the ICP call of every run: the mean per  */
 /* run, in milliseconds, and how many runs it covers.  Synchronises with the last of them.  This is how bench.py measures   */

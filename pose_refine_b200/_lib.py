@@ -74,6 +74,7 @@ PROTOTYPES = {
     "pr_refiner_run": (_i, [_vp, _vp, _sz, Criteria, _vp, _vp]),
     "pr_refiner_run_device": (_i, [_vp, _vp, _sz, Criteria, _vp, _vp]),
     "pr_refiner_buffers": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "pr_refiner_overflow_flag": (_i, [_vp, C.POINTER(_vp)]),
     "pr_refiner_scene_buffers": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "pr_refiner_stage_ms": (_i, [_vp, C.POINTER(_f), C.POINTER(_f), C.POINTER(_u32)]),
     "pr_launch_count": (C.c_uint64, []),

@@ -619,6 +619,13 @@ class PoseRefiner:
               "pr_refiner_run_device")
         return results_dev
 
+    def overflowed(self):
+        """True when a cloud of the last run did not fit capacity_points (pr_refiner_overflow_flag; synchronises)."""
+        p = C.c_void_p()
+        check(lib().pr_refiner_overflow_flag(self._h, C.byref(p)), "pr_refiner_overflow_flag")
+        torch.cuda.synchronize()
+        return bool(torch.as_tensor(_CudaView(p.value, (1,), "<i4"), device="cuda").item())
+
     def stage_ms(self):
         """(mean render->cloud ms, mean ICP ms, number of runs) of the runs since the last call, from the CUDA events the
         refiner records around its two stages."""

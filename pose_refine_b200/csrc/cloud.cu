@@ -112,21 +112,25 @@ __global__ void __launch_bounds__(kSegThreads)
 cloud_offsets_kernel(uint32_t* __restrict__ counts, uint32_t n, uint32_t align, unsigned long long capacity,
                      uint32_t* __restrict__ offsets, uint32_t* __restrict__ overflow) {
     __shared__ unsigned s_warp[kSegThreads / 32];
-    unsigned carry = 0;
+    // offsets are 32-bit: a batch whose padded clouds add up to more than 2^32 - 1 points cannot be addressed, whatever the
+    // capacity says ("unlimited" included) -- the clouds past that point are dropped and flagged like any other overflow
+    if (capacity > 0xFFFFFFFFull) capacity = 0xFFFFFFFFull;
+    unsigned long long carry = 0;
     bool spilled = false;
     for (uint32_t b = 0; b < n; b += kSegThreads) {
         const uint32_t i = b + threadIdx.x;
         unsigned v = (i < n) ? counts[i] : 0u;
-        v = (v + align - 1) / align * align;
+        v = (v + align - 1) / align * align;           // the entry points reject batches whose 256-image block totals could wrap
         unsigned total;
         const unsigned excl = block_excl_scan(v, s_warp, &total);
         if (i < n) {
-            offsets[i] = carry + excl;
-            if ((unsigned long long)carry + excl + v > capacity) { counts[i] = 0; spilled = true; }
+            const unsigned long long at = carry + excl;
+            offsets[i] = (uint32_t)(at > 0xFFFFFFFFull ? 0xFFFFFFFFull : at);
+            if (at + v > capacity) { counts[i] = 0; spilled = true; }
         }
         carry += total;
     }
-    if (threadIdx.x == 0) offsets[n] = carry;
+    if (threadIdx.x == 0) offsets[n] = (uint32_t)(carry > 0xFFFFFFFFull ? 0xFFFFFFFFull : carry);
     if (overflow) {
         if (threadIdx.x == 0) *overflow = 0;
         __syncthreads();
@@ -287,6 +291,7 @@ int cloud_from_tiles(const int32_t* depth_dev, size_t n_images, uint32_t width, 
                      uint32_t* counts_dev, uint32_t* offsets_dev, uint32_t* overflow_dev, size_t capacity_points,
                      uint32_t align_points, float* out_pts_dev, cudaStream_t stream) {
     if (tile_w != 64 || tile_h % 32 != 0 || tile_h > 128) return PR_ERR_UNSUPPORTED;       // the fill kernel's thread -> pixel map
+    if (((size_t)width * height + align_points) * (n_images < 256 ? n_images : 256) > 0xFFFFFFFFull) return PR_ERR_INVALID_ARGUMENT;   // 32-bit block totals of the offset scan
     const uint32_t n_tiles = (uint32_t)(tiles_x * tiles_y);
     // scratch behind the offsets: list of non-empty tiles per image, then the list lengths (see cloud_tiles_scratch_words)
     unsigned* tile_list = tile_off + n_images * (size_t)n_tiles;
@@ -325,6 +330,7 @@ int pr_depth2cloud_count(const void* depth_dev, int depth_is_int32, size_t n_ima
     if (align_points == 0 || width == 0 || height == 0) return PR_ERR_INVALID_ARGUMENT;
     const size_t n_px = (size_t)width * height;
     if (n_px > 0x7FFFFFFFull || n_images > 65535) return PR_ERR_INVALID_ARGUMENT;
+    if ((n_px + align_points) * (n_images < 256 ? n_images : 256) > 0xFFFFFFFFull) return PR_ERR_INVALID_ARGUMENT;   // 32-bit block totals of the offset scan
     if (workspace_bytes < pr_depth2cloud_workspace_bytes(n_images, width, height)) return PR_ERR_WORKSPACE_TOO_SMALL;
     cudaStream_t stream = as_stream(stream_);
     const uint32_t n_seg = (uint32_t)((n_px + kSegPx - 1) / kSegPx);
@@ -361,10 +367,10 @@ int pr_depth2cloud_fill(const void* depth_dev, int depth_is_int32, size_t n_imag
     const dim3 grid(n_seg, (unsigned)n_images);
     if (depth_is_int32)
         cloud_fill_kernel<int32_t><<<grid, kSegThreads, 0, stream>>>((const int32_t*)depth_dev, width, (uint32_t)n_px, n_seg, seg,
-                                                                    offsets_dev, Ki, tl_x, tl_y, out_pts_dev, capacity_points, vec);
+                                                                    offsets_dev, Ki, tl_x, tl_y, out_pts_dev, capacity_points ? capacity_points : ~(size_t)0, vec);
     else
         cloud_fill_kernel<uint16_t><<<grid, kSegThreads, 0, stream>>>((const uint16_t*)depth_dev, width, (uint32_t)n_px, n_seg, seg,
-                                                                     offsets_dev, Ki, tl_x, tl_y, out_pts_dev, capacity_points, vec);
+                                                                     offsets_dev, Ki, tl_x, tl_y, out_pts_dev, capacity_points ? capacity_points : ~(size_t)0, vec);
     count_launch();
     PR_LAUNCH_CHECK();
     return PR_OK;

@@ -327,6 +327,12 @@ int pr_refiner_buffers(pr_refiner* r, const int32_t** depth_dev, const float** p
     return PR_OK;
 }
 
+int pr_refiner_overflow_flag(pr_refiner* r, const uint32_t** flag_dev) {
+    if (!r || !flag_dev) return PR_ERR_INVALID_ARGUMENT;
+    *flag_dev = r->d_overflow;
+    return PR_OK;
+}
+
 int pr_refiner_stage_ms(pr_refiner* r, float* render_cloud_ms, float* icp_ms, uint32_t* n_runs) {
     if (!r) return PR_ERR_INVALID_ARGUMENT;
     double a = 0.0, b = 0.0;

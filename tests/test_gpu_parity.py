@@ -663,6 +663,12 @@ def test_refiner_capacity_overflow_is_reported(api, mesh, fixture_scene, golden)
     with pytest.raises(PoseRefineError) as e:
         ref.run(arrays["hyp8"], api.ICPConvergenceCriteria(0.0, 0.0, 2))
     assert e.value.status == -4
+    # the device-resident call has no status to return it in: the flag on the device says so, the clouds that did not fit
+    # come back empty (fitness 0, identity), the ones that did are refined as usual
+    import torch
+    res = ref.run_device(torch.as_tensor(arrays["hyp8"].reshape(8, 16)).cuda(), api.ICPConvergenceCriteria(0.0, 0.0, 2)).cpu().numpy()
+    assert ref.overflowed()
+    assert res[0, 17] > 0.5 and (res[2:, 17] == 0).all() and np.array_equal(res[7, :16].reshape(4, 4), np.eye(4, dtype=np.float32))
     ref.close()
 
 
