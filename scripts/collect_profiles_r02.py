@@ -59,7 +59,7 @@ def main():
         launches.append((r[ix["Kernel Name"]].split("(")[0].replace("void ", ""), v))
     # the refiner steps: vertex_kernel ... icp_hyp_kernel groups; take the LAST complete step before the stage timings
     names = [n for n, _ in launches]
-    step_end = max(i for i, n in enumerate(names[:len(names)]) if "icp_hyp_kernel" in n and i > 0 and "cloud_fill_tiles" in names[i - 1])
+    step_end = max(i for i, n in enumerate(names) if "icp_hyp_kernel" in n and i > 1 and "icp_order_kernel" in names[i - 1] and "cloud_fill_tiles" in names[i - 2])
     step_start = max(i for i in range(step_end) if "vertex_kernel" in names[i])
     step = launches[step_start:step_end + 1]
     tot = sum(v for _, v in step)
@@ -68,8 +68,15 @@ def main():
                 "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` (cold-cache, serialised: compare SHARES, not absolutes).\n\n"
                 "## one refiner step (pr_refiner_run_device), in launch order\n\n| kernel | us | share of the step |\n|---|---:|---:|\n")
         for n, v in step: f.write(f"| {n} | {v:.1f} | {100 * v / tot:.1f}% |\n")
-        f.write(f"\nTotal {tot:.1f} us in {len(step)} launches (+ 2 memsets).  Live in bench.py (CUDA events inside the timed steps): ICP 1.43 ms of a 2.56 ms step = 56 %; "
-                f"here {100 * step[-1][1] / tot:.1f} %.\n\n## all launches of the capture, aggregated\n\n| kernel | launches | total us | mean us |\n|---|---:|---:|---:|\n")
+        live = ""
+        try:
+            import json
+            bj = json.loads(open(os.path.join(P, "r02_bench_1gpu.json")).read().strip().splitlines()[-1])
+            live = (f"  Live in bench.py (CUDA events inside the timed steps): ICP {bj['stages']['icp_ms']:.2f} ms of a {bj['ms_per_step']:.2f} ms step = "
+                    f"{100 * bj['stages']['icp_ms'] / bj['ms_per_step']:.0f} %; here {100 * step[-1][1] / tot:.1f} %.")
+        except Exception:
+            pass
+        f.write(f"\nTotal {tot:.1f} us in {len(step)} launches (+ 1 memset).{live}\n\n## all launches of the capture, aggregated\n\n| kernel | launches | total us | mean us |\n|---|---:|---:|---:|\n")
         agg = collections.OrderedDict()
         for n, v in launches:
             a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += v
