@@ -243,10 +243,13 @@ int pr_scene_nn_build(const void* depth_dev, int depth_is_int32, uint32_t width,
 /* scene_pixels: width*height of the projective scene the workspace will be used with; for Scene_nn pass   */
 /* n_points + 2*n_nodes + 16 (room for the re-laid-out kd-tree; with less, the reference-layout walk is used). */
 size_t pr_icp_workspace_bytes(size_t n_hyp, size_t capacity_points, size_t scene_pixels);
-/* kd-tree scenes: the same plus one int per model point, in which every pass leaves the index of its nearest          */
-/* neighbour; the next pass starts its search from that point (the pose moves little between passes, so the walk only   */
-/* has to prove the candidate: 3-4x fewer node visits; the result is the same exact nearest neighbour).                 */
-/* pr_icp_nn_batch uses it when the workspace is at least this large.                                                   */
+/* kd-tree scenes: the same plus (a) one int per model point, in which every pass leaves the index of its nearest       */
+/* neighbour; the next pass starts its tree walk from that point (the pose moves little between passes, so the walk     */
+/* only has to prove the candidate: 3-4x fewer node visits), and (b) room for a hash grid over the scene points (a      */
+/* table of 2 n slots, 8 n points of 16 bytes, build scratch: ~200 bytes per scene point) that answers every query      */
+/* nearer than half a grid cell to its neighbour without the tree.  The result is the same exact nearest neighbour      */
+/* either way; pr_icp_nn_batch uses whichever of the two the workspace has room for (a workspace sized by               */
+/* pr_icp_workspace_bytes still works, without either).  Asynchronous on `stream` (round 1 synchronised here).          */
 size_t pr_icp_nn_workspace_bytes(size_t n_hyp, size_t capacity_points, size_t n_scene_points, size_t n_nodes);
 int pr_icp_projective_batch(float* pts_dev, const uint32_t* offsets_dev, const uint32_t* counts_dev, size_t n_hyp,
                             size_t capacity_points, const pr_scene_projective* scene, pr_icp_criteria criteria,
