@@ -328,8 +328,10 @@ def run_ours(args):
         alg = (ITERS + 1) * (12 * n_pts + w * h * 24 + 72 * n_hyp)
         achieved = alg / (ms * 1e-3) / 1e9
         return {"bound": "hbm", "kernel": f"icp_hyp_kernel<PackedScene> ({what}; one launch = 31 passes over all hypotheses)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "traffic_source": "not measurable in-run; dram__bytes of one launch: profiles/r02_ncu_icp_hyp.txt",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_dram_bytes(os.path.join(ROOT, "profiles", "r02_ncu_icp_hyp.txt")) if what.startswith("C2") else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this workload, read from the committed "
+                                  "`ncu --set full` summary profiles/r02_ncu_icp_hyp.txt (scripts/gpu_profiles.sh); DRAM bytes cannot be measured in-run",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "launch_ms": ms, "note": how}
 
     def icp_roofline(refiner, n_hyp, w, h, what):
@@ -358,7 +360,7 @@ def run_ours(args):
         achieved = alg / (ms * 1e-3) / 1e9
         return ms, n_pts, {"bound": "hbm", "kernel": f"icp_hyp_kernel<PackedScene> ({what}; one launch = 31 passes over all hypotheses)",
                            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                           "traffic_source": "not measurable in-run; dram__bytes of one launch: profiles/r02_ncu_icp_hyp.txt",
+                           "traffic_source": "no ncu capture of this configuration (the C2 capture is profiles/r02_ncu_icp_hyp.txt)",
                            "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "launch_ms": ms,
                            "note": "mean CUDA-event time of pr_icp_projective_batch_packed on the clouds the fused render->cloud call "
                                    "produced, 256 MB written between repetitions so that the clouds start in HBM"}
@@ -533,6 +535,22 @@ def ref_cuda_build(n_hyp):
                 "pose_max_abs_diff_vs_ours_converged": top.get("pose_max_abs_diff_vs_ours_converged")}
     except Exception as e:      # a measurement aid must never take the bench line down
         return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
+def ncu_dram_bytes(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel in a profiles/*.txt summary written by
+    scripts/collect_profiles_r02.py from an `ncu --set full` capture (one launch); None when the file or the lines are missing."""
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    total, seen = 0.0, 0
+    try:
+        for ln in open(path):
+            parts = ln.split()
+            if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and parts[-1] in scale:
+                total += float(parts[-2].replace(",", "")) * scale[parts[-1]]
+                seen += 1
+    except OSError:
+        return None
+    return total if seen == 2 else None
 
 
 def main():

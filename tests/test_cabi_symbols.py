@@ -156,3 +156,15 @@ def test_header_is_plain_c(tmp_path):
                 ["/usr/bin/g++", "-std=c++14", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)]):
         res = subprocess.run(cmd, capture_output=True, text=True)
         assert res.returncode == 0, res.stderr
+
+
+def test_bench_reads_roofline_traffic_from_the_committed_ncu_summary():
+    """bench.py's roofline.traffic is the DRAM byte count of one launch from the committed `ncu --set full` summary,
+    not a constant in the code: the parser finds both counters in profiles/r02_ncu_icp_hyp.txt and scales their units."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    got = bench.ncu_dram_bytes(os.path.join(ROOT, "profiles", "r02_ncu_icp_hyp.txt"))
+    assert got is not None and 1e8 < got < 4.5e9          # below the 4.41 GB algorithmic bytes: the clouds stay in L2
+    assert bench.ncu_dram_bytes(os.path.join(ROOT, "profiles", "does_not_exist.txt")) is None
