@@ -229,8 +229,16 @@ cloud_fill_tiles_kernel(const int32_t* __restrict__ depth, uint32_t width, uint3
     __syncthreads();
     unsigned done = 0;                                            // points of this tile written by earlier 32-row bands
    for (int band = 0; band < tile_h; band += 32) {
-    const uint32_t v = ty * tile_h + band + (threadIdx.x >> 3);   // 8 threads per tile row, 32 rows per band
-    const uint32_t u0 = tx * 64 + (threadIdx.x & 7) * 8;
+    // A warp covers 4 tile rows x 64 columns; lane l takes the 8 pixels of row (l & 3), column chunk (l >> 2), so that 32
+    // CONSECUTIVE POINTS of the cloud are an 8 x 4 pixel block, not a 32 x 1 strip: the 32 lanes of an ICP warp then look up
+    // neighbours in two dimensions -- the same few tree nodes / grid blocks / scene sectors (PR_CLOUD_STRIPS: the old order).
+#ifdef PR_CLOUD_STRIPS
+    const uint32_t row_in_band = threadIdx.x >> 3, chunk = threadIdx.x & 7;
+#else
+    const uint32_t row_in_band = (threadIdx.x >> 5) * 4 + (threadIdx.x & 3), chunk = (threadIdx.x & 31) >> 2;
+#endif
+    const uint32_t v = ty * tile_h + band + row_in_band;          // 32 rows per band
+    const uint32_t u0 = tx * 64 + chunk * 8;
     const int32_t* img = depth + (size_t)image * width * height;
     int d[kPxPerThread];
     unsigned c = 0;
@@ -267,8 +275,8 @@ cloud_fill_tiles_kernel(const int32_t* __restrict__ depth, uint32_t width, uint3
         if (d[k] > 0) {
             // icp.cu:249-251
             const float z = divf((float)d[k], 1000.0f);
-            sp[3 * slot + 0] = mulf(s_fx[(threadIdx.x & 7) * 8 + k], z);
-            sp[3 * slot + 1] = mulf(s_fy[band + (threadIdx.x >> 3)], z);
+            sp[3 * slot + 0] = mulf(s_fx[chunk * 8 + k], z);
+            sp[3 * slot + 1] = mulf(s_fy[band + row_in_band], z);
             sp[3 * slot + 2] = z;
             slot++;
         }

@@ -120,7 +120,7 @@ def test_render_indexed_mesh_bit_exact(api, port, mesh, golden):
 
 def test_render_cloud_fused_matches_render_then_depth2cloud(api, port, mesh, golden):
     """pr_render_cloud_batch: the depth batch is the rasteriser's, bit for bit; every cloud holds exactly the points
-    depth2cloud_cpu (icp.cpp:73-117) makes from that depth image (same float values), in screen-tile order; offsets are
+    depth2cloud_cpu (icp.cpp:73-117) makes from that depth image (same float values), in screen-tile / 8x4-block order; offsets are
     aligned; an odd image size (partial tiles at the right and bottom edge) and an empty pose are covered."""
     arrays, scal = golden
     K = arrays["K"]
@@ -146,16 +146,14 @@ def test_render_cloud_fused_matches_render_then_depth2cloud(api, port, mesh, gol
             # same multiset of points: sort both by (y, x) -- within an image the (x, y) pair identifies the pixel
             ks, kg = np.lexsort((want[:, 0], want[:, 1])), np.lexsort((got[:, 0], got[:, 1]))
             assert np.array_equal(want[ks], got[kg]), f"pose {i}: fused cloud differs from depth2cloud of the same depth"
-            if W == 640 and counts[i]:
-                # tile order: the first point lies in the first non-empty 64x64 tile (row-major tiles)
+            if counts[i]:
+                # the order itself: 64x64 screen tiles row-major; inside a tile 32-row bands, 4-row strips, and in a strip 8-pixel
+                # column chunks each taken 4 rows deep -- 32 consecutive points are an 8 x 4 pixel block (cloud.cu)
                 ys, xs = np.nonzero(want_depth[i])
-                tiles = (ys // 64) * 10 + xs // 64
-                first = tiles.min()
-                sel = tiles == first
-                y0, x0 = ys[sel].min(), None
-                x0 = xs[sel & (ys == y0)].min()
-                z = np.float32(want_depth[i][y0, x0]) / np.float32(1000.0)
-                assert got[0, 2] == z
+                tiles_x = (W + 63) // 64
+                key = np.lexsort((xs % 8, ys % 4, (xs % 64) // 8, (ys % 32) // 4, (ys % 64) // 32, (ys // 64) * tiles_x + xs // 64))
+                z = want_depth[i][ys[key], xs[key]].astype(np.float32) / np.float32(1000.0)
+                assert np.array_equal(got[:, 2], z), f"pose {i}: cloud order"
 
 
 def test_render_clustered_edge_cases(api, port, golden):
