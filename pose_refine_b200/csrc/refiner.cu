@@ -179,6 +179,21 @@ int pr_refiner_create(pr_refiner** out, const float* tris_host, size_t n_tris, u
     size_t n_clusters = 0;
     rc = pr_mesh_cluster(verts.data(), r->n_verts, faces.data(), n_tris, cl_off.data(), cl_verts.data(), &n_clusters);
     if (rc != PR_OK) { delete r; return rc; }
+#ifndef PR_NO_VERTEX_RENUMBER
+    {   // Renumber the vertices in the order the clusters first use them: a cluster's vertex list then reads (mostly) consecutive
+        // projected vertices -- whole 32-byte sectors instead of one 16-byte vertex per sector in cluster_span_kernel, and the
+        // three vertices of a triangle sit near each other for the tile kernel.  Same triangles, same coordinates: same depth.
+        std::vector<int32_t> new_id(r->n_verts, -1);
+        int32_t next = 0;
+        for (int32_t i = 0; i < cl_off[n_clusters]; i++) if (new_id[cl_verts[i]] < 0) new_id[cl_verts[i]] = next++;
+        for (size_t v = 0; v < r->n_verts; v++) if (new_id[v] < 0) new_id[v] = next++;       // vertices no face uses
+        std::vector<float> moved(r->n_verts * 3);
+        for (size_t v = 0; v < r->n_verts; v++) memcpy(&moved[3 * (size_t)new_id[v]], &verts[3 * v], 12);
+        memcpy(verts.data(), moved.data(), r->n_verts * 12);
+        for (size_t i = 0; i < 3 * n_tris; i++) faces[i] = new_id[faces[i]];
+        for (int32_t i = 0; i < cl_off[n_clusters]; i++) cl_verts[i] = new_id[cl_verts[i]];
+    }
+#endif
     r->ws_render_bytes = pr_render_cloud_workspace_bytes(max_hyp, r->n_verts, n_tris, width, height);
     r->ws_cloud_bytes = pr_depth2cloud_workspace_bytes(max_hyp, width, height);
     r->ws_icp_bytes = pr_icp_workspace_bytes(max_hyp, r->capacity_points, 3 * n_px + 16);   // projective: n_px; kd-tree: <= n_px points + 2 * (2 n_px + 1) nodes... bounded by 3 n_px for leaf >= 2
