@@ -1217,7 +1217,7 @@ inline GridWs carve_grid(void* base, size_t n_points) {
     g.counts = (unsigned*)take(slots * 4);
     g.cursor = (unsigned*)take(slots * 4);
     g.pt_slot = (unsigned*)take(8 * n_points * 4);
-    g.gpts = (float4*)take(8 * n_points * 16);
+    g.gpts = (float4*)take((8 * n_points + 8) * 16);      // + the elements the last list's vector loads may touch
     g.bytes = used;
     return g;
 }

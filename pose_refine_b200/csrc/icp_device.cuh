@@ -386,15 +386,25 @@ __device__ __forceinline__ bool nn_grid_query(const PackedNnScene& s, const NnGr
     const float4* __restrict__ list = s.grid.gpts + (v.y >> 8);
     if (COUNT) tests += cnt;
     float best = fminf(g.r_ok_sq, s.max_dist_sq);
-    float4 q = __ldg(list);                       // cnt >= 1: a block exists only where a point does
-    for (unsigned j = 0; j < cnt; j++) {
-        const float4 nxt = __ldg(list + min(j + 1, cnt - 1));      // the next point is on its way while this one is tested
-        const int i = __float_as_int(q.w);
-        const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
-        const float d2 = addf(addf(mulf(dx, dx), mulf(dy, dy)), mulf(dz, dz));    // pcd_scene.h:86-89
-        if (d2 < best) { best = d2; best_i = i; }
-        else if (d2 == best && best_i >= 0 && i != best_i && nn_visited_first(s.ref, px, py, pz, i, best_i)) best_i = i;
-        q = nxt;
+    // four points per step: their loads are in flight together (the elements behind a list are the next list's points or the
+    // pad behind the last list, so the loads need no bound; the tests do)
+#ifndef PR_NN_LIST_ILP
+#define PR_NN_LIST_ILP 4
+#endif
+    for (unsigned j = 0; j < cnt; j += PR_NN_LIST_ILP) {
+        float4 q[PR_NN_LIST_ILP];
+#pragma unroll
+        for (int k = 0; k < PR_NN_LIST_ILP; k++) q[k] = __ldg(list + j + k);
+#pragma unroll
+        for (int k = 0; k < PR_NN_LIST_ILP; k++) {
+            const float dx = px - q[k].x, dy = py - q[k].y, dz = pz - q[k].z;
+            const float d2 = addf(addf(mulf(dx, dx), mulf(dy, dy)), mulf(dz, dz));    // pcd_scene.h:86-89
+            if (d2 <= best && j + k < cnt) {
+                const int i = __float_as_int(q[k].w);
+                if (d2 < best) { best = d2; best_i = i; }
+                else if (best_i >= 0 && i != best_i && nn_visited_first(s.ref, px, py, pz, i, best_i)) best_i = i;
+            }
+        }
     }
     return cnt != 255u && best_i >= 0;
 }
@@ -463,12 +473,25 @@ __device__ __forceinline__ int nn_search_packed_t(const PackedNnScene& s, float 
             const int a = __float_as_int(lo.w);
             const int left = a & 0xFFFFFF, cnt = (a >> 24) & 127;
             if (COUNT) tests += (unsigned)cnt;
-            for (int i = left; i < left + cnt; i++) {
-                const float4 q = __ldg(s.pts4 + i);
-                const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
-                const float d2 = addf(addf(mulf(dx, dx), mulf(dy, dy)), mulf(dz, dz));    // pcd_scene.h:86-89
-                if (d2 < best) { best = d2; best_i = i; }
-                else if (d2 == best && best_i >= 0 && i != best_i && nn_visited_first(s.ref, px, py, pz, i, best_i)) best_i = i;
+#ifndef PR_NN_LEAF_ILP
+#define PR_NN_LEAF_ILP 2
+#endif
+            // PR_NN_LEAF_ILP points per step, their loads in flight together (behind the points of the last leaf lie the
+            // packed nodes: the loads need no bound, the tests do)
+            for (int i0 = left; i0 < left + cnt; i0 += PR_NN_LEAF_ILP) {
+                float4 q[PR_NN_LEAF_ILP];
+#pragma unroll
+                for (int k = 0; k < PR_NN_LEAF_ILP; k++) q[k] = __ldg(s.pts4 + i0 + k);
+#pragma unroll
+                for (int k = 0; k < PR_NN_LEAF_ILP; k++) {
+                    const int i = i0 + k;
+                    const float dx = px - q[k].x, dy = py - q[k].y, dz = pz - q[k].z;
+                    const float d2 = addf(addf(mulf(dx, dx), mulf(dy, dy)), mulf(dz, dz));    // pcd_scene.h:86-89
+                    if (d2 <= best && i < left + cnt) {
+                        if (d2 < best) { best = d2; best_i = i; }
+                        else if (best_i >= 0 && i != best_i && nn_visited_first(s.ref, px, py, pz, i, best_i)) best_i = i;
+                    }
+                }
             }
         }
         go = pop();
